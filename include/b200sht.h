@@ -1,0 +1,198 @@
+/*
+ * b200sht -- C ABI of the B200-native spherical-harmonic hot path (RealSHT / InverseRealSHT / SpectralConv).
+ *
+ * Nothing equivalent exists in the reference: NVIDIA/makani has no native code and reaches this
+ * arithmetic through the Python package torch-harmonics.  Each entry point below names the reference interface
+ * it replaces (paths relative to /root/reference):
+ *
+ *   b200sht_plan_create          <- torch_harmonics.RealSHT.__init__ / InverseRealSHT.__init__ as constructed at
+ *                                   makani/models/networks/sfnonet.py:792-805 (Legendre table + quadrature precompute)
+ *   b200sht_sht_forward          <- RealSHT.forward            (call site makani/models/common/spectral_convolution.py:239)
+ *   b200sht_sht_inverse          <- InverseRealSHT.forward     (call sites spectral_convolution.py:241,253)
+ *   b200sht_sht_forward_adjoint  <- autograd backward of RealSHT.forward (rfft + einsum adjoints)
+ *   b200sht_sht_inverse_adjoint  <- autograd backward of InverseRealSHT.forward
+ *   b200sht_mix_forward/backward <- makani/models/common/contractions.py:19-54 (_contract_* einsums) and :62-151
+ *   b200sht_spectral_conv_forward<- SpectralConv.forward       (spectral_convolution.py:213-264), one call
+ *   b200sht_complex_relu_*       <- makani/models/common/activations.py:88-127 (ComplexReLU)
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative b200sht_status otherwise; b200sht_last_error() gives text.
+ *   - all data pointers are DEVICE pointers owned by the caller (e.g. the PyTorch caching allocator) unless a
+ *     parameter is documented as host memory.  The library allocates only inside plans (Legendre table, FFT
+ *     twiddles, TMA descriptors).
+ *   - every launch takes the cudaStream_t to enqueue on (as void*), is asynchronous and never synchronises.
+ *   - plans are immutable after creation and may be shared by concurrent calls on different streams.
+ *   - no thread-local state except the last-error string.
+ *
+ * Internal ("packed") tensor formats -- opaque to callers that only use the *_sht_* / spectral_conv entry points,
+ * documented in DESIGN.md section 3:
+ *   latspec  float [mmax][2][B*C][kp]           (after the longitude FFT;  kp = nlat rounded up to 8)
+ *   spec     float [lmax][mmax][2][B][cp]       (spectral coefficients;    cp = C rounded up to 4)
+ */
+#ifndef B200SHT_H
+#define B200SHT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200SHT_OK = 0,
+  B200SHT_ERR_INVALID = -1,      /* bad argument (shape, dtype, null pointer)            */
+  B200SHT_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed                    */
+  B200SHT_ERR_UNSUPPORTED = -3,  /* valid request this build cannot serve (e.g. FFT len) */
+  B200SHT_ERR_NOMEM = -4
+} b200sht_status;
+
+typedef enum { B200SHT_F32 = 0, B200SHT_BF16 = 1 } b200sht_dtype;
+
+/* arithmetic of the Legendre / channel-mix contractions */
+typedef enum {
+  B200SHT_PREC_FP32 = 0, /* fp32 FMA on CUDA cores (reference tests run with TF32 disabled)          */
+  B200SHT_PREC_TF32 = 1  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (reference training: allow_tf32) */
+} b200sht_precision;
+
+typedef enum {
+  B200SHT_OP_DHCONV = 0,      /* weight [G][Ci][Co][L]        contractions.py:23  */
+  B200SHT_OP_DIAGONAL = 1,    /* weight [G][Ci][Co][L][M]     contractions.py:19  */
+  B200SHT_OP_SEP_DHCONV = 2,  /* weight [G][Ci][L]            contractions.py:31  */
+  B200SHT_OP_SEP_DIAGONAL = 3,/* weight [G][Ci][L][M]         contractions.py:27  */
+  B200SHT_OP_SHARED = 4,      /* weight [Ci][Co]              contractions.py:62  (compl_mul2d_fwd)     */
+  B200SHT_OP_LDEP = 5         /* weight [L][Ci][Co]           contractions.py:106 (compl_exp_mul2d_fwd) */
+} b200sht_mix_op;
+
+typedef struct b200sht_plan b200sht_plan;
+
+const char* b200sht_last_error(void);
+int b200sht_version(void);
+
+/* ---------------------------------------------------------------------------------------------- plan */
+/* cost/quad_w: HOST arrays [nlat]: cos(colatitude) in row order (row 0 = north) and quadrature weights on [-1,1].
+ * The Legendre table P[m][l][k] (orthonormal, optional Condon-Shortley phase) is built on the device in fp64
+ * and stored as fp32 [mmax][lmax][kp]. */
+int b200sht_plan_create(b200sht_plan** plan, int nlat, int nlon, int lmax, int mmax,
+                        const double* cost, const double* quad_w, int csphase, void* stream);
+int b200sht_plan_destroy(b200sht_plan* plan);
+/* what: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 path available (0/1) */
+int64_t b200sht_plan_query(const b200sht_plan* plan, int what);
+/* device pointer to the fp32 table [mmax][lmax][kp] (for tests) */
+const float* b200sht_plan_table(const b200sht_plan* plan);
+/* copy the table into caller-owned device memory (mmax*lmax*kp floats) */
+int b200sht_plan_copy_table(const b200sht_plan* plan, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------ packed-format sizes */
+int64_t b200sht_latspec_elems(const b200sht_plan* plan, int B, int C); /* floats in a latspec buffer */
+int64_t b200sht_spec_elems(const b200sht_plan* plan, int B, int C);    /* floats in a spec buffer    */
+int64_t b200sht_spec_elems_lm(int L, int M, int B, int C);
+
+/* ------------------------------------------------------------------------------------ stage kernels */
+/* Longitude analysis: real rows -> truncated half spectrum.
+ *   X[m][p][r][k] = row_scale[k] * mode_scale[m] * sum_j x[r][k][j] exp(-2 pi i m j / nlon)
+ * scale_mode 0: SHT forward     (row_scale = quad_w[k] * 2 pi / nlon, mode_scale = 1)
+ * scale_mode 1: adjoint of irfft (row_scale = 1, mode_scale = 1 for m = 0 and Nyquist, 2 otherwise) */
+int b200sht_fft_analysis(const b200sht_plan* plan, const void* x, int dtype, int B, int C,
+                         float* latspec, int scale_mode, void* stream);
+/* Longitude synthesis: truncated half spectrum -> real rows (+ optional per-channel bias, cast to dtype).
+ * scale_mode 0: irfft(norm="forward") semantics (imaginary part of m=0 / Nyquist ignored)
+ * scale_mode 1: adjoint of the scale_mode-0 analysis (row_scale = quad_w[k] 2 pi/nlon, modes m>0 halved) */
+int b200sht_fft_synthesis(const b200sht_plan* plan, const float* latspec, void* y, int dtype, int B, int C,
+                          const float* bias, int scale_mode, void* stream);
+/* Legendre analysis  spec[l][m][..] = sum_k P[m][l][k] latspec[m][..][k]   (l >= 32*floor(m/32)) */
+int b200sht_legendre_analysis(const b200sht_plan* plan, const float* latspec, float* spec, int B, int C,
+                              int precision, void* stream);
+/* Legendre synthesis latspec[m][..][k] = sum_l P[m][l][k] spec[l][m][..] */
+int b200sht_legendre_synthesis(const b200sht_plan* plan, const float* spec, float* latspec, int B, int C,
+                               int precision, void* stream);
+/* packed spec [L][M][2][B][cp] <-> torch complex64 [B*C][L][M] (exact zeros written for l < m).  These and the
+ * mix / ComplexReLU entry points below depend only on the mode counts (L, M), not on a grid, so they take no plan. */
+int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream);
+int b200sht_spec_pack(int L, int M, const void* coeffs, float* spec, int B, int C, void* stream);
+
+/* ------------------------------------------------------------------------- torch-harmonics boundary */
+/* bytes of scratch the four calls below need for (B, C) */
+int64_t b200sht_sht_workspace_bytes(const b200sht_plan* plan, int B, int C);
+/* x [B*C][nlat][nlon] (dtype) -> coeffs complex64 [B*C][lmax][mmax] */
+int b200sht_sht_forward(const b200sht_plan* plan, const void* x, int dtype, int B, int C, void* coeffs,
+                        void* workspace, int precision, void* stream);
+/* coeffs complex64 [B*C][lmax][mmax] -> y [B*C][nlat][nlon] (dtype) */
+int b200sht_sht_inverse(const b200sht_plan* plan, const void* coeffs, void* y, int dtype, int B, int C,
+                        void* workspace, int precision, void* stream);
+/* gradient of sht_forward w.r.t. x given dL/dcoeffs (PyTorch complex-gradient convention) */
+int b200sht_sht_forward_adjoint(const b200sht_plan* plan, const void* gcoeffs, void* gx, int dtype, int B, int C,
+                                void* workspace, int precision, void* stream);
+/* gradient of sht_inverse w.r.t. coeffs given dL/dy */
+int b200sht_sht_inverse_adjoint(const b200sht_plan* plan, const void* gy, int dtype, int B, int C, void* gcoeffs,
+                                void* workspace, int precision, void* stream);
+
+/* -------------------------------------------------------------------------------------- channel mix */
+/* weight re-layout: native torch parameter (complex64, shapes per b200sht_mix_op) -> packed
+ * float [L][G][Ci/G][cop][2] (cop = Co/G rounded up to 2; l-stride 0 for OP_SHARED).  Only the dense
+ * operators (DHCONV, SHARED, LDEP) use a packed weight; the others read the native layout. */
+int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co);
+int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, void* stream);
+int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int L, int G, int Ci, int Co, void* stream);
+
+/* y[l][m][.][b][o] = sum_i x[l][m][.][b][i] * w[...]   on packed spec tensors (x: C = Ci, y: C = Co).
+ * w: packed weight for dense ops, native complex64 for DIAGONAL / SEP_* ops.
+ * cbias (OP_SHARED / OP_LDEP only, may be null): complex64 [Co] added to every mode (compl_muladd2d_fwd). */
+int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, const void* cbias,
+                        float* y, int B, int G, int Ci, int Co, int precision, void* stream);
+/* gx = dL/dx (may be null), gw = dL/dw in the same format as w (may be null; overwritten, not accumulated),
+ * gcbias complex64 [Co] (may be null). */
+int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, const float* gy,
+                         float* gx, void* gw, void* gcbias, int B, int G, int Ci, int Co, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------- ComplexReLU */
+/* mode 0 real, 1 cartesian, 2 modulus, 3 halfplane (activations.py:88-127) on a packed spec tensor.
+ * bias: float [C] (modes 2,3; null -> 0).  In-place allowed (y == x). */
+int b200sht_complex_relu_forward(int L, int M, int mode, const float* x, const float* bias,
+                                 float negative_slope, float* y, int B, int C, void* stream);
+int b200sht_complex_relu_backward(int L, int M, int mode, const float* x, const float* bias,
+                                  float negative_slope, const float* gy, float* gx, float* gbias, int B, int C,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------ SpectralConv, one call */
+typedef struct {
+  int B, Cin, Cout, G;
+  int op;          /* b200sht_mix_op */
+  int dtype;       /* activation dtype of x / y / residual */
+  int precision;   /* b200sht_precision */
+} b200sht_conv_desc;
+int64_t b200sht_spectral_conv_workspace_bytes(const b200sht_plan* fwd, const b200sht_plan* inv, const b200sht_conv_desc* d);
+/* y = iSHT(W . SHT(x)) (+bias); residual (may be null) = iSHT(SHT(x)).  w: packed for dense ops, native otherwise.
+ * spec_x_saved (may be null): packed spec buffer that receives SHT(x) for the backward pass. */
+int b200sht_spectral_conv_forward(const b200sht_plan* fwd, const b200sht_plan* inv, const b200sht_conv_desc* d,
+                                  const void* x, const void* w, const float* bias, void* y, void* residual,
+                                  float* spec_x_saved, void* workspace, void* stream);
+/* gy, gresidual (may be null) -> gx, gw (same format as w), gbias float [Cout] (may be null) */
+int b200sht_spectral_conv_backward(const b200sht_plan* fwd, const b200sht_plan* inv, const b200sht_conv_desc* d,
+                                   const void* gy, const void* gresidual, const float* spec_x_saved, const void* w,
+                                   void* gx, void* gw, float* gbias, void* workspace, void* stream);
+
+/* sum over batch and latitude of latspec[m=0][re][b][c][k]: d(loss)/d(bias) when latspec = fft_analysis(gy, mode 1) */
+int b200sht_bias_grad(const b200sht_plan* plan, const float* latspec, float* gbias, int B, int C, void* stream);
+
+/* host-buffer convenience (end-to-end path for FFI users): copies x (pinned or pageable HOST memory) to the
+ * device, runs b200sht_spectral_conv_forward, copies y back.  Synchronises the stream before returning. */
+int b200sht_spectral_conv_forward_host(const b200sht_plan* fwd, const b200sht_plan* inv, const b200sht_conv_desc* d,
+                                       const void* x_host, const void* w_device, const float* bias_device,
+                                       void* y_host, void* stream);
+
+/* ------------------------------------------------------------------- debug / CPU-testable entry points
+ * These run the SAME __host__ __device__ code as the kernels on the host, so the FFT plan / butterflies / pair
+ * splitting and the Legendre recurrence are unit-tested without a GPU.  All pointers are HOST pointers. */
+/* direction 0: rows a, b (float[N]) -> half spectra Xa, Xb (float[2*mmax], interleaved), unscaled rfft.
+ * direction 1: half spectra (float[2*mmax]) -> rows (float[N]), irfft(norm="forward") semantics. */
+int b200sht_debug_fft_host(int N, int mmax, int direction, const float* in_a, const float* in_b, float* out_a, float* out_b);
+/* radices chosen for length N; returns the number of stages or a negative status */
+int b200sht_debug_fft_plan(int N, int* radices, int max_radices);
+/* table [mmax][lmax][nlat] (fp32) from cos(colatitude) cost[nlat] */
+int b200sht_debug_table_host(int nlat, int lmax, int mmax, const double* cost, int csphase, float* table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SHT_H */

@@ -1,0 +1,446 @@
+// C ABI of the b200sht library (see include/b200sht.h for the contract and the reference interfaces replaced).
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace b200sht {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+// other translation units
+bool make_fft_plan(int N, FftPlan* p);
+int build_table(Plan* pl, const double* d_cost, cudaStream_t st);
+int fft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int scale_mode, cudaStream_t st);
+int fft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int scale_mode, cudaStream_t st);
+int legendre_analysis_simt(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
+int legendre_synthesis_simt(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st);
+int spec_unpack(const Plan* pl, const float* spec, void* coeffs, int B, int C, cudaStream_t st);
+int spec_pack(const Plan* pl, const void* coeffs, float* spec, int B, int C, cudaStream_t st);
+int bias_grad(const Plan* pl, const float* X, float* gbias, int B, int C, cudaStream_t st);
+int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, cudaStream_t st);
+int mix_forward_simt(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
+int mix_backward_simt(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
+                      int Ci, int Co, cudaStream_t st);
+int complex_relu_fwd(const Plan* pl, int mode, const float* x, const float* bias, float slope, float* y, int B, int C, cudaStream_t st);
+int complex_relu_bwd(const Plan* pl, int mode, const float* x, const float* bias, float slope, const float* gy, float* gx, float* gbias, int B,
+                     int C, cudaStream_t st);
+// tcgen05 path (umma.cu)
+int umma_plan_init(Plan* pl);
+void umma_plan_destroy(Plan* pl);
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st);
+int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
+int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
+                      int Ci, int Co, cudaStream_t st);
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static inline int cp_of(int C) { return round_up(C, 4); }
+// dims-only plan for the entry points that depend on (L, M) alone
+static inline Plan lm_plan(int L, int M) { Plan p; memset(&p, 0, sizeof(p)); p.lmax = L; p.mmax = M; return p; }
+int umma_available();
+
+}  // namespace b200sht
+
+using namespace b200sht;
+
+extern "C" {
+
+const char* b200sht_last_error(void) { return g_last_error.c_str(); }
+int b200sht_version(void) { return 100; }
+
+int b200sht_plan_create(b200sht_plan** out, int nlat, int nlon, int lmax, int mmax, const double* cost, const double* quad_w, int csphase,
+                        void* stream) {
+  B200_REQUIRE(out != nullptr && cost != nullptr && quad_w != nullptr, "plan_create: null argument");
+  B200_REQUIRE(nlat >= 2 && nlon >= 2 && lmax >= 1 && mmax >= 1, "plan_create: bad sizes nlat=%d nlon=%d lmax=%d mmax=%d", nlat, nlon, lmax, mmax);
+  B200_REQUIRE(mmax <= nlon / 2 + 1, "plan_create: mmax=%d exceeds nlon/2+1=%d", mmax, nlon / 2 + 1);
+  b200sht_plan* pl = new b200sht_plan();
+  memset(static_cast<Plan*>(pl), 0, sizeof(Plan));
+  pl->nlat = nlat; pl->nlon = nlon; pl->lmax = lmax; pl->mmax = mmax; pl->kp = round_up(nlat, 8); pl->csphase = csphase;
+  if (!make_fft_plan(nlon, &pl->fft)) {
+    set_error("plan_create: nlon=%d has a prime factor > 13 (unsupported FFT length)", nlon);
+    delete pl;
+    return B200SHT_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = S(stream);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const size_t tbytes = sizeof(float) * (size_t)mmax * lmax * pl->kp;
+  double* d_cost = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_table, tbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_rowscale, sizeof(float) * pl->kp);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_twiddle, sizeof(float2) * nlon);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cost, sizeof(double) * nlat);
+  if (e != cudaSuccess) {
+    set_error("plan_create: allocation failed: %s", cudaGetErrorString(e));
+    cudaFree(pl->d_table); cudaFree(pl->d_rowscale); cudaFree(pl->d_twiddle); cudaFree(d_cost);
+    delete pl;
+    return B200SHT_ERR_NOMEM;
+  }
+  std::vector<float> rs(pl->kp, 0.f);
+  for (int k = 0; k < nlat; ++k) rs[k] = (float)(quad_w[k] * 2.0 * M_PI / (double)nlon);
+  std::vector<float2> tw(nlon);
+  for (int t = 0; t < nlon; ++t) {
+    const double ang = -2.0 * M_PI * (double)t / (double)nlon;
+    tw[t] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  int rc = 0;
+  do {
+    if ((e = cudaMemcpyAsync(pl->d_rowscale, rs.data(), sizeof(float) * pl->kp, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(pl->d_twiddle, tw.data(), sizeof(float2) * nlon, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(d_cost, cost, sizeof(double) * nlat, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    rc = build_table(pl, d_cost, st);
+    if (rc) break;
+    // host staging vectors go out of scope: wait for the copies (plan creation is not on the hot path)
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  cudaFree(d_cost);
+  if (e != cudaSuccess || rc != 0) {
+    if (e != cudaSuccess) set_error("plan_create: %s", cudaGetErrorString(e));
+    cudaFree(pl->d_table); cudaFree(pl->d_rowscale); cudaFree(pl->d_twiddle);
+    delete pl;
+    return rc ? rc : B200SHT_ERR_CUDA;
+  }
+  pl->umma_ok = (umma_plan_init(pl) == 0) ? 1 : 0;
+  *out = pl;
+  return 0;
+}
+
+int b200sht_plan_destroy(b200sht_plan* pl) {
+  if (!pl) return 0;
+  umma_plan_destroy(pl);
+  cudaFree(pl->d_table);
+  cudaFree(pl->d_rowscale);
+  cudaFree(pl->d_twiddle);
+  delete pl;
+  return 0;
+}
+
+int64_t b200sht_plan_query(const b200sht_plan* pl, int what) {
+  if (!pl) return -1;
+  switch (what) {
+    case 0: return pl->nlat;
+    case 1: return pl->nlon;
+    case 2: return pl->lmax;
+    case 3: return pl->mmax;
+    case 4: return pl->kp;
+    case 5: return (int64_t)sizeof(float) * pl->mmax * pl->lmax * pl->kp;
+    case 6: return pl->umma_ok;
+    default: return -1;
+  }
+}
+
+const float* b200sht_plan_table(const b200sht_plan* pl) { return pl ? pl->d_table : nullptr; }
+int b200sht_plan_copy_table(const b200sht_plan* pl, float* dst, void* stream) {
+  B200_REQUIRE(pl && dst, "plan_copy_table: null argument");
+  B200_CHECK_CUDA(cudaMemcpyAsync(dst, pl->d_table, sizeof(float) * (size_t)pl->mmax * pl->lmax * pl->kp, cudaMemcpyDeviceToDevice, S(stream)));
+  return 0;
+}
+
+int64_t b200sht_latspec_elems(const b200sht_plan* pl, int B, int C) { return (int64_t)pl->mmax * 2 * B * C * pl->kp; }
+int64_t b200sht_spec_elems(const b200sht_plan* pl, int B, int C) { return (int64_t)pl->lmax * pl->mmax * 2 * B * cp_of(C); }
+int64_t b200sht_spec_elems_lm(int L, int M, int B, int C) { return (int64_t)L * M * 2 * B * cp_of(C); }
+
+// -------------------------------------------------------------------------------------------- stages
+int b200sht_fft_analysis(const b200sht_plan* pl, const void* x, int dtype, int B, int C, float* latspec, int scale_mode, void* stream) {
+  B200_REQUIRE(pl && x && latspec, "fft_analysis: null argument");
+  B200_REQUIRE(scale_mode == 0 || scale_mode == 1, "fft_analysis: bad scale_mode %d", scale_mode);
+  return fft_analysis(pl, x, dtype, B, C, latspec, scale_mode, S(stream));
+}
+
+int b200sht_fft_synthesis(const b200sht_plan* pl, const float* latspec, void* y, int dtype, int B, int C, const float* bias, int scale_mode,
+                          void* stream) {
+  B200_REQUIRE(pl && y && latspec, "fft_synthesis: null argument");
+  B200_REQUIRE(scale_mode == 0 || scale_mode == 1, "fft_synthesis: bad scale_mode %d", scale_mode);
+  return fft_synthesis(pl, latspec, y, dtype, B, C, bias, scale_mode, S(stream));
+}
+
+static int check_precision(int umma_ok, int precision, const char* who) {
+  if (precision == B200SHT_PREC_FP32) return 0;
+  if (precision == B200SHT_PREC_TF32) {
+    if (!umma_ok) {
+      set_error("%s: the tcgen05 (TF32) path is not available on this device/build; refusing to fall back silently", who);
+      return B200SHT_ERR_UNSUPPORTED;
+    }
+    return 0;
+  }
+  set_error("%s: unknown precision %d", who, precision);
+  return B200SHT_ERR_INVALID;
+}
+
+int b200sht_legendre_analysis(const b200sht_plan* pl, const float* latspec, float* spec, int B, int C, int precision, void* stream) {
+  B200_REQUIRE(pl && latspec && spec && B > 0 && C > 0, "legendre_analysis: bad argument");
+  int rc = check_precision(pl->umma_ok, precision, "legendre_analysis");
+  if (rc) return rc;
+  return precision == B200SHT_PREC_TF32 ? legendre_analysis_umma(pl, latspec, spec, B, C, S(stream))
+                                        : legendre_analysis_simt(pl, latspec, spec, B, C, S(stream));
+}
+
+int b200sht_legendre_synthesis(const b200sht_plan* pl, const float* spec, float* latspec, int B, int C, int precision, void* stream) {
+  B200_REQUIRE(pl && latspec && spec && B > 0 && C > 0, "legendre_synthesis: bad argument");
+  int rc = check_precision(pl->umma_ok, precision, "legendre_synthesis");
+  if (rc) return rc;
+  return precision == B200SHT_PREC_TF32 ? legendre_synthesis_umma(pl, spec, latspec, B, C, S(stream))
+                                        : legendre_synthesis_simt(pl, spec, latspec, B, C, S(stream));
+}
+
+int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_unpack: bad argument");
+  Plan p = lm_plan(L, M);
+  return spec_unpack(&p, spec, coeffs, B, C, S(stream));
+}
+int b200sht_spec_pack(int L, int M, const void* coeffs, float* spec, int B, int C, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_pack: bad argument");
+  Plan p = lm_plan(L, M);
+  return spec_pack(&p, coeffs, spec, B, C, S(stream));
+}
+
+int b200sht_bias_grad(const b200sht_plan* pl, const float* latspec, float* gbias, int B, int C, void* stream) {
+  B200_REQUIRE(pl && latspec && gbias, "bias_grad: null argument");
+  return bias_grad(pl, latspec, gbias, B, C, S(stream));
+}
+
+// ------------------------------------------------------------------------- torch-harmonics boundary
+static inline size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+int64_t b200sht_sht_workspace_bytes(const b200sht_plan* pl, int B, int C) {
+  return (int64_t)(align256(sizeof(float) * b200sht_latspec_elems(pl, B, C)) + align256(sizeof(float) * b200sht_spec_elems(pl, B, C)));
+}
+
+static void split_ws(const b200sht_plan* pl, int B, int C, void* ws, float** latspec, float** spec) {
+  *latspec = static_cast<float*>(ws);
+  *spec = reinterpret_cast<float*>(static_cast<char*>(ws) + align256(sizeof(float) * b200sht_latspec_elems(pl, B, C)));
+}
+
+int b200sht_sht_forward(const b200sht_plan* pl, const void* x, int dtype, int B, int C, void* coeffs, void* ws, int precision, void* stream) {
+  B200_REQUIRE(pl && x && coeffs && ws, "sht_forward: null argument");
+  float *X, *sp;
+  split_ws(pl, B, C, ws, &X, &sp);
+  int rc = b200sht_fft_analysis(pl, x, dtype, B, C, X, 0, stream);
+  if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
+  if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, coeffs, B, C, stream);
+  return rc;
+}
+
+int b200sht_sht_inverse(const b200sht_plan* pl, const void* coeffs, void* y, int dtype, int B, int C, void* ws, int precision, void* stream) {
+  B200_REQUIRE(pl && y && coeffs && ws, "sht_inverse: null argument");
+  float *Z, *sp;
+  split_ws(pl, B, C, ws, &Z, &sp);
+  int rc = b200sht_spec_pack(pl->lmax, pl->mmax, coeffs, sp, B, C, stream);
+  if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, Z, y, dtype, B, C, nullptr, 0, stream);
+  return rc;
+}
+
+int b200sht_sht_forward_adjoint(const b200sht_plan* pl, const void* gcoeffs, void* gx, int dtype, int B, int C, void* ws, int precision,
+                                void* stream) {
+  B200_REQUIRE(pl && gx && gcoeffs && ws, "sht_forward_adjoint: null argument");
+  float *Z, *sp;
+  split_ws(pl, B, C, ws, &Z, &sp);
+  int rc = b200sht_spec_pack(pl->lmax, pl->mmax, gcoeffs, sp, B, C, stream);
+  if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, Z, gx, dtype, B, C, nullptr, 1, stream);
+  return rc;
+}
+
+int b200sht_sht_inverse_adjoint(const b200sht_plan* pl, const void* gy, int dtype, int B, int C, void* gcoeffs, void* ws, int precision,
+                                void* stream) {
+  B200_REQUIRE(pl && gy && gcoeffs && ws, "sht_inverse_adjoint: null argument");
+  float *X, *sp;
+  split_ws(pl, B, C, ws, &X, &sp);
+  int rc = b200sht_fft_analysis(pl, gy, dtype, B, C, X, 1, stream);
+  if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
+  if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, gcoeffs, B, C, stream);
+  return rc;
+}
+
+// --------------------------------------------------------------------------------------- channel mix
+int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co) {
+  if (G <= 0 || Ci % G || Co % G) return -1;
+  const int64_t Cig = Ci / G, Cog = Co / G, cop = round_up((int)Cog, 2);
+  switch (op) {
+    case B200SHT_OP_DHCONV: return (int64_t)L * G * Cig * cop * 2;
+    case B200SHT_OP_LDEP: return (int64_t)L * Cig * cop * 2;
+    case B200SHT_OP_SHARED: return Cig * cop * 2;
+    case B200SHT_OP_DIAGONAL: return (int64_t)G * Cig * Cog * L * M * 2;
+    case B200SHT_OP_SEP_DHCONV: return (int64_t)G * Cig * L * 2;
+    case B200SHT_OP_SEP_DIAGONAL: return (int64_t)G * Cig * L * M * 2;
+    default: return -1;
+  }
+}
+
+int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, void* stream) {
+  B200_REQUIRE(w_native && w_packed, "mix_weight_pack: null argument");
+  return mix_weight_relayout(op, w_native, w_packed, L, G, Ci, Co, 0, S(stream));
+}
+int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int L, int G, int Ci, int Co, void* stream) {
+  B200_REQUIRE(w_native && w_packed, "mix_weight_unpack: null argument");
+  return mix_weight_relayout(op, w_native, const_cast<float*>(w_packed), L, G, Ci, Co, 1, S(stream));
+}
+
+static bool dense_op(int op) { return op == B200SHT_OP_DHCONV || op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP; }
+
+int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co,
+                        int precision, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && x && w && y, "mix_forward: bad argument");
+  int rc = check_precision(umma_available(), precision, "mix_forward");
+  if (rc) return rc;
+  Plan p = lm_plan(L, M);
+  const Plan* pl = &p;
+  if (precision == B200SHT_PREC_TF32 && dense_op(op)) return mix_forward_umma(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));
+  return mix_forward_simt(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));  // per-mode operators are bandwidth bound: one path
+}
+
+int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B,
+                         int G, int Ci, int Co, int precision, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && w && gy, "mix_backward: bad argument");
+  B200_REQUIRE(gw == nullptr || x != nullptr, "mix_backward: weight gradient needs x");
+  int rc = check_precision(umma_available(), precision, "mix_backward");
+  if (rc) return rc;
+  Plan p = lm_plan(L, M);
+  const Plan* pl = &p;
+  if (precision == B200SHT_PREC_TF32 && dense_op(op)) return mix_backward_umma(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
+  return mix_backward_simt(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
+}
+
+int b200sht_complex_relu_forward(int L, int M, int mode, const float* x, const float* bias, float slope, float* y, int B, int C,
+                                 void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && x && y, "complex_relu_forward: bad argument");
+  Plan p = lm_plan(L, M);
+  return complex_relu_fwd(&p, mode, x, bias, slope, y, B, C, S(stream));
+}
+int b200sht_complex_relu_backward(int L, int M, int mode, const float* x, const float* bias, float slope, const float* gy, float* gx,
+                                  float* gbias, int B, int C, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && x && gy && gx, "complex_relu_backward: bad argument");
+  Plan p = lm_plan(L, M);
+  return complex_relu_bwd(&p, mode, x, bias, slope, gy, gx, gbias, B, C, S(stream));
+}
+
+// ---------------------------------------------------------------------------- SpectralConv, one call
+struct ConvWs {
+  float *lat_in, *spec_in, *spec_out, *lat_out;
+  size_t total;
+};
+
+static ConvWs conv_ws(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, void* base) {
+  ConvWs w;
+  const int Cmax = d->Cin > d->Cout ? d->Cin : d->Cout;
+  size_t off = 0;
+  char* b = static_cast<char*>(base);
+  w.lat_in = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * b200sht_latspec_elems(f, d->B, Cmax));
+  w.spec_in = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * b200sht_spec_elems(f, d->B, Cmax));
+  w.spec_out = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * b200sht_spec_elems(f, d->B, Cmax));
+  w.lat_out = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * b200sht_latspec_elems(v, d->B, Cmax));
+  w.total = off;
+  return w;
+}
+
+static int check_conv(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d) {
+  B200_REQUIRE(f && v && d, "spectral_conv: null argument");
+  B200_REQUIRE(f->lmax == v->lmax && f->mmax == v->mmax, "spectral_conv: forward (%d,%d) and inverse (%d,%d) mode counts differ", f->lmax, f->mmax,
+               v->lmax, v->mmax);
+  B200_REQUIRE(d->B > 0 && d->G > 0 && d->Cin % d->G == 0 && d->Cout % d->G == 0, "spectral_conv: channels (%d,%d) not divisible by groups %d", d->Cin,
+               d->Cout, d->G);
+  return 0;
+}
+
+int64_t b200sht_spectral_conv_workspace_bytes(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d) {
+  if (check_conv(f, v, d)) return -1;
+  return (int64_t)conv_ws(f, v, d, nullptr).total;
+}
+
+int b200sht_spectral_conv_forward(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, const void* x, const void* w,
+                                  const float* bias, void* y, void* residual, float* spec_x_saved, void* workspace, void* stream) {
+  int rc = check_conv(f, v, d);
+  if (rc) return rc;
+  B200_REQUIRE(x && w && y && workspace, "spectral_conv_forward: null argument");
+  ConvWs ws = conv_ws(f, v, d, workspace);
+  float* spec_x = spec_x_saved ? spec_x_saved : ws.spec_in;
+  rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0, stream);
+  if (!rc) rc = b200sht_legendre_analysis(f, ws.lat_in, spec_x, d->B, d->Cin, d->precision, stream);
+  if (!rc && residual) {
+    rc = b200sht_legendre_synthesis(v, spec_x, ws.lat_out, d->B, d->Cin, d->precision, stream);
+    if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0, stream);
+  }
+  if (!rc) rc = b200sht_mix_forward(f->lmax, f->mmax, d->op, spec_x, w, nullptr, ws.spec_out, d->B, d->G, d->Cin, d->Cout, d->precision, stream);
+  if (!rc) rc = b200sht_legendre_synthesis(v, ws.spec_out, ws.lat_out, d->B, d->Cout, d->precision, stream);
+  if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, y, d->dtype, d->B, d->Cout, bias, 0, stream);
+  return rc;
+}
+
+// elementwise accumulate of two packed spec tensors (residual-path gradient)
+__global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, const void* gy, const void* gresidual,
+                                   const float* spec_x_saved, const void* w, void* gx, void* gw, float* gbias, void* workspace, void* stream) {
+  int rc = check_conv(f, v, d);
+  if (rc) return rc;
+  B200_REQUIRE(gy && w && workspace, "spectral_conv_backward: null argument");
+  B200_REQUIRE(gw == nullptr || spec_x_saved != nullptr, "spectral_conv_backward: weight gradient needs the saved spectrum");
+  ConvWs ws = conv_ws(f, v, d, workspace);
+  // dL/d(spec_out) = analysis_v(fft_v(gy, adjoint scaling))
+  rc = b200sht_fft_analysis(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, 1, stream);
+  if (!rc && gbias) rc = b200sht_bias_grad(v, ws.lat_out, gbias, d->B, d->Cout, stream);
+  if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cout, d->precision, stream);
+  if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, gx ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G, d->Cin, d->Cout,
+                                     d->precision, stream);
+  if (!rc && gx) {
+    if (gresidual) {
+      rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1, stream);
+      if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cin, d->precision, stream);
+      if (!rc) {
+        const long long n = b200sht_spec_elems(f, d->B, d->Cin);
+        axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(ws.spec_in, ws.spec_out, n);
+        B200_CHECK_LAUNCH();
+      }
+    }
+    if (!rc) rc = b200sht_legendre_synthesis(f, ws.spec_in, ws.lat_in, d->B, d->Cin, d->precision, stream);
+    if (!rc) rc = b200sht_fft_synthesis(f, ws.lat_in, gx, d->dtype, d->B, d->Cin, nullptr, 1, stream);
+  }
+  return rc;
+}
+
+int b200sht_spectral_conv_forward_host(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, const void* x_host,
+                                       const void* w_device, const float* bias_device, void* y_host, void* stream) {
+  int rc = check_conv(f, v, d);
+  if (rc) return rc;
+  B200_REQUIRE(x_host && w_device && y_host, "spectral_conv_forward_host: null argument");
+  const size_t esz = d->dtype == B200SHT_BF16 ? 2 : 4;
+  const size_t xin = esz * (size_t)d->B * d->Cin * f->nlat * f->nlon, yout = esz * (size_t)d->B * d->Cout * v->nlat * v->nlon;
+  const size_t wsb = conv_ws(f, v, d, nullptr).total;
+  char* dev = nullptr;
+  cudaStream_t st = S(stream);
+  B200_CHECK_CUDA(cudaMallocAsync(&dev, align256(xin) + align256(yout) + wsb, st));
+  void* dx = dev;
+  void* dy = dev + align256(xin);
+  void* dws = dev + align256(xin) + align256(yout);
+  cudaError_t e = cudaMemcpyAsync(dx, x_host, xin, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rc = b200sht_spectral_conv_forward(f, v, d, dx, w_device, bias_device, dy, nullptr, nullptr, dws, stream);
+    if (!rc) e = cudaMemcpyAsync(y_host, dy, yout, cudaMemcpyDeviceToHost, st);
+  }
+  cudaFreeAsync(dev, st);
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    set_error("spectral_conv_forward_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return B200SHT_ERR_CUDA;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Shared helpers for the b200sht library (error reporting, packed-format index math).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/b200sht.h"
+
+#define HD __host__ __device__ __forceinline__
+
+namespace b200sht {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::b200sht::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));  \
+      return B200SHT_ERR_CUDA;                                                                     \
+    }                                                                                              \
+  } while (0)
+
+#define B200_CHECK_LAUNCH()  B200_CHECK_CUDA(cudaGetLastError())
+
+#define B200_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::b200sht::set_error(__VA_ARGS__);        \
+      return B200SHT_ERR_INVALID;               \
+    }                                           \
+  } while (0)
+
+HD int round_up(int a, int b) { return (a + b - 1) / b * b; }
+HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Block-triangular storage convention: for order m only degrees l >= lstart(m) are
+// stored/computed, for degree l only orders m < mend(l).  Entries with lstart(m) <= l < m hold exact zeros.
+constexpr int kTriBlock = 32;
+HD int lstart(int m) { return (m / kTriBlock) * kTriBlock; }
+HD int mend(int l, int M) { int e = (l / kTriBlock + 1) * kTriBlock; return e < M ? e : M; }
+
+struct FftPlan {
+  int N;
+  int nstages;
+  int radix[20];
+};
+
+// The immutable plan object behind b200sht_plan.
+struct Plan {
+  int nlat, nlon, lmax, mmax, kp;
+  int csphase;
+  float* d_table;       // [mmax][lmax][kp]
+  float* d_rowscale;    // [kp]  quad_w[k] * 2 pi / nlon (0 in the padding)
+  float2* d_twiddle;    // [nlon] exp(-2 pi i t / nlon)
+  FftPlan fft;
+  int sm_count;
+  int umma_ok;          // tcgen05 path usable on this device
+  void* umma_state;     // TMA descriptors etc. (owned by umma translation unit)
+};
+
+}  // namespace b200sht
+
+struct b200sht_plan : public b200sht::Plan {};
