@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- one SFNO SpectralConv block, forward + backward, on synthetic ERA5-shaped input.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (N > 1 under torchrun) prints ONE JSON line on rank 0.
+  metric    SFNO-block fwd+bwd samples/sec (BASELINE.json), workload = configs[1]: 721x1440x73ch, bf16, batch 1 per GPU
+  value     device-resident input, CUDA-event timed, max over ranks
+  e2e       same step through the public nn.Module with the input in pinned HOST memory (H2D of x and D2H of the weight
+            gradient inside the timed region)
+  roofline  dominant kernel (largest share of the step), algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (restatement of torch-harmonics + makani einsums) on this box's host cores (bounded sample)
+`--impl reference` times that CPU implementation alone (the reference has no other implementation of this path that can run
+here: torch-harmonics is not installable).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nlat_in, nlon_in, grid_in, nlat_out, nlon_out, grid_out, lmax, mmax, C)
+    "sfno_block_721x1440x73": (721, 1440, "equiangular", 721, 1440, "equiangular", 240, 241, 73),       # BASELINE configs[1] (SURVEY cfg 2c)
+    "sfno_block_240x480x384": (240, 480, "legendre-gauss", 240, 480, "legendre-gauss", 240, 241, 384),  # interior SFNO block (cfg 2a)
+    "sfno_block_721to240x384": (721, 1440, "equiangular", 240, 480, "legendre-gauss", 240, 241, 384),  # first SFNO block (cfg 2b)
+    "tiny": (33, 64, "equiangular", 33, 64, "equiangular", 16, 17, 8),
+}
+
+
+def nnz_modes(L, M):
+    return sum(max(0, L - m) for m in range(M))
+
+
+def stage_bytes(wl, act_bytes):
+    """Algorithmic HBM bytes per launch of each stage, B = 1."""
+    nlat_i, nlon_i, _, nlat_o, nlon_o, _, L, M, C = WORKLOADS[wl]
+    nnz = nnz_modes(L, M)
+    spec = C * nnz * 8  # complex fp32 coefficients, l >= m only
+    w = C * C * L * 8
+    return {
+        "fft_analysis_in": C * nlat_i * nlon_i * act_bytes + C * nlat_i * M * 8,
+        "legendre_analysis_in": C * nlat_i * M * 8 + nnz * nlat_i * 4 + spec,
+        "mix_forward": 2 * spec + w,
+        "legendre_synthesis_out": spec + nnz * nlat_o * 4 + C * nlat_o * M * 8,
+        "fft_synthesis_out": C * nlat_o * M * 8 + C * nlat_o * nlon_o * act_bytes,
+        "fft_analysis_out": C * nlat_o * nlon_o * act_bytes + C * nlat_o * M * 8,
+        "legendre_analysis_out": C * nlat_o * M * 8 + nnz * nlat_o * 4 + spec,
+        "mix_backward": 3 * spec + 2 * w,
+        "legendre_synthesis_in": spec + nnz * nlat_i * 4 + C * nlat_i * M * 8,
+        "fft_synthesis_in": C * nlat_i * M * 8 + C * nlat_i * nlon_i * act_bytes,
+    }
+
+
+def flops_fwd_bwd(wl):
+    nlat_i, _, _, nlat_o, _, _, L, M, C = WORKLOADS[wl]
+    nnz = nnz_modes(L, M)
+    leg = lambda nlat: 4 * C * nlat * nnz
+    return 2 * (leg(nlat_i) + leg(nlat_o)) + 3 * 8 * C * C * nnz
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def build_oracle_block(wl, dtype=torch.float32):
+    from oracle import makani_oracle as O
+
+    nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, L, M, C = WORKLOADS[wl]
+    sht = O.RealSHT(nlat_i, nlon_i, L, M, grid_i, dtype=dtype)
+    isht = O.InverseRealSHT(nlat_o, nlon_o, L, M, grid_o, dtype=dtype)
+    return O, sht, isht
+
+
+def cpu_reference_steps(wl, steps, warmup, act_dtype=torch.bfloat16):
+    """fwd+bwd of the block through the CPU oracle (restated torch-harmonics + makani SpectralConv), all host threads."""
+    O, sht, isht = build_oracle_block(wl)
+    nlat_i, nlon_i, _, nlat_o, nlon_o, _, L, M, C = WORKLOADS[wl]
+    torch.manual_seed(333)
+    w = (math.sqrt(1.0 / C) * torch.randn(1, C, C, L, dtype=torch.complex64)).requires_grad_(True)
+    x = torch.randn(1, C, nlat_i, nlon_i).to(act_dtype).requires_grad_(True)
+    gy = torch.randn(1, C, nlat_o, nlon_o).to(act_dtype)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        y, _ = O.spectral_conv_forward(x, w, sht, isht, operator_type="dhconv")
+        y.backward(gy)
+        x.grad = None
+        w.grad = None
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps = max(1, args.steps)
+    t = cpu_reference_steps(wl, steps, min(args.warmup, 1))
+    val = 1.0 / t
+    line = {
+        "impl": "reference", "metric": "SFNO-block fwd+bwd samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": wl, "batch_per_gpu": 1, "activations": "bf16", "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full fwd+bwd steps of the workload through oracle/makani_oracle.py (torch.fft + torch.einsum, fp32, {cores} threads)"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+
+    import makani_b200 as mb
+    from makani_b200 import _lib
+    from makani_b200.sht import _ptr, _stream, _dtype_code
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, L, M, C = WORKLOADS[wl]
+    act_dtype = torch.bfloat16 if args.act == "bf16" else torch.float32
+    act_bytes = 2 if act_dtype == torch.bfloat16 else 4
+
+    f = mb.RealSHT(nlat_i, nlon_i, L, M, grid_i)
+    i = mb.InverseRealSHT(nlat_o, nlon_o, L, M, grid_o)
+    plan_f, plan_i = f.plan(dev), i.plan(dev)
+    precision = args.precision
+    if precision == "best":
+        precision = "tf32" if plan_f.umma_ok else "fp32"
+    f.precision = i.precision = precision
+    torch.manual_seed(333 + rank)
+    conv = mb.SpectralConv(f, i, C, C, operator_type="dhconv", precision=precision).to(dev)
+    conv._wcache.enabled = False  # weights change every optimizer step in training: re-layout inside the timed step
+    x_host = torch.randn(1, C, nlat_i, nlon_i).to(act_dtype).pin_memory()
+    x_dev = x_host.to(dev)
+    gy = torch.randn(1, C, nlat_o, nlon_o, device=dev).to(act_dtype)
+    gw_host = torch.empty(conv.weight.shape, dtype=torch.complex64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(xin):
+        xin.requires_grad_(True)
+        conv.weight.grad = None
+        y, _ = conv(xin)
+        y.backward(gy)
+        g = xin.grad
+        xin.grad = None
+        xin.requires_grad_(False)
+        return g
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        step(xd)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(conv.weight.grad))
+        gw_host.copy_(conv.weight.grad, non_blocking=True)
+
+    def timed(fn, steps, warmup, use_flush=True):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = []
+        for _ in range(steps):
+            if use_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def dp_step():
+        step(x_dev)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(conv.weight.grad))
+
+    # kernel launches of OUR library inside one step (counted by the ctypes call wrapper)
+    counter = {"n": 0}
+    kernels_per_call = {"b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1,
+                        "b200sht_mix_forward": 1, "b200sht_mix_backward": 2, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
+                        "b200sht_bias_grad": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1}
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        counter["n"] += kernels_per_call.get(name, 0)
+        return orig_call(name, *a)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev = None
+    try:
+        import makani_b200.sht as _s, makani_b200.spectral_convolution as _c
+        dp_step()  # first call builds plans / tables
+        torch.cuda.synchronize()
+        _lib.call = counting_call
+        counter["n"] = 0
+        dp_step()
+        launches_per_step = counter["n"]
+        _lib.call = orig_call
+        if sampler:
+            sampler.start()
+        ms_dev = timed(dp_step, args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else None
+        ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), use_flush=True)
+    finally:
+        _lib.call = orig_call
+
+    # ---- per-stage kernel timings (CUDA events, L2 flushed before each launch) -> roofline
+    stages = {}
+    if rank == 0 and not args.no_stages:
+        st = _stream(dev)
+        prec = mb.resolve_precision(precision)
+        B = 1
+        lat_i = torch.empty(plan_f.latspec_elems(B, C), device=dev)
+        lat_o = torch.empty(plan_i.latspec_elems(B, C), device=dev)
+        sp_a = torch.zeros(plan_f.spec_elems(B, C), device=dev)
+        sp_b = torch.zeros(plan_f.spec_elems(B, C), device=dev)
+        sp_c = torch.zeros(plan_f.spec_elems(B, C), device=dev)
+        wpk = conv._wcache.get(conv.weight, _lib.OP_DHCONV, L, M, 1, C, C)
+        gwpk = torch.empty_like(wpk)
+        y_dev = torch.empty(1, C, nlat_o, nlon_o, device=dev, dtype=act_dtype)
+        gx_dev = torch.empty_like(x_dev)
+        dt = _dtype_code(act_dtype)
+        VP0 = mb.sht._VP(0)
+        calls = {
+            "fft_analysis_in": lambda: _lib.call("b200sht_fft_analysis", plan_f.handle, _ptr(x_dev), dt, B, C, _ptr(lat_i), 0, st),
+            "legendre_analysis_in": lambda: _lib.call("b200sht_legendre_analysis", plan_f.handle, _ptr(lat_i), _ptr(sp_a), B, C, prec, st),
+            "mix_forward": lambda: _lib.call("b200sht_mix_forward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), VP0, _ptr(sp_b), B, 1, C, C, prec, st),
+            "legendre_synthesis_out": lambda: _lib.call("b200sht_legendre_synthesis", plan_i.handle, _ptr(sp_b), _ptr(lat_o), B, C, prec, st),
+            "fft_synthesis_out": lambda: _lib.call("b200sht_fft_synthesis", plan_i.handle, _ptr(lat_o), _ptr(y_dev), dt, B, C, VP0, 0, st),
+            "fft_analysis_out": lambda: _lib.call("b200sht_fft_analysis", plan_i.handle, _ptr(gy), dt, B, C, _ptr(lat_o), 1, st),
+            "legendre_analysis_out": lambda: _lib.call("b200sht_legendre_analysis", plan_i.handle, _ptr(lat_o), _ptr(sp_b), B, C, prec, st),
+            "mix_backward": lambda: _lib.call("b200sht_mix_backward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), _ptr(sp_b), _ptr(sp_c), _ptr(gwpk), VP0, B, 1, C, C, prec, st),
+            "legendre_synthesis_in": lambda: _lib.call("b200sht_legendre_synthesis", plan_f.handle, _ptr(sp_c), _ptr(lat_i), B, C, prec, st),
+            "fft_synthesis_in": lambda: _lib.call("b200sht_fft_synthesis", plan_f.handle, _ptr(lat_i), _ptr(gx_dev), dt, B, C, VP0, 1, st),
+        }
+        sb = stage_bytes(wl, act_bytes)
+        for name, fn in calls.items():
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(max(3, min(args.steps, 10))):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sum(ts) / len(ts)
+            stages[name] = {"ms": round(ms, 4), "alg_MB": round(sb[name] / 1e6, 2), "GBps": round(sb[name] / ms / 1e6, 1)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    roof = None
+    if stages:
+        top = max(stages, key=lambda k: stages[k]["ms"])
+        roof = {"bound": "hbm", "kernel": top, "achieved": stages[top]["GBps"], "peak": peak, "unit": "GB/s", "frac": round(stages[top]["GBps"] / peak, 4),
+                "traffic": None, "peak_source": peak_src, "kernel_ms": stages[top]["ms"], "sum_stage_ms": round(sum(s["ms"] for s in stages.values()), 3)}
+
+    # CPU baseline beside it (bounded sample: 1 warm-up + 2 timed steps of the same workload)
+    cores = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu:
+        torch.set_num_threads(cores)
+        t = cpu_reference_steps(wl, 2, 1, act_dtype)
+        cpu = {"value": 1.0 / t, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"2 full fwd+bwd steps of {wl} through oracle/makani_oracle.py (torch.fft + torch.einsum fp32, {cores} threads), {t:.2f} s/step"}
+
+    x_bytes = x_host.numel() * x_host.element_size()
+    line = {
+        "metric": "SFNO-block fwd+bwd samples/sec", "value": world * 1e3 / ms_dev, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if precision == "tf32" else "f32",
+        "data": "synthetic",
+        "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": "tcgen05 kind::tf32, fp32 accumulate" if precision == "tf32" else "fp32 FMA (CUDA cores)",
+                   "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "operator": "dhconv", "lmax": L, "mmax": M,
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush); inputs 151 MB > 126 MB L2",
+                   "weight_relayout_in_step": True, "flops_fwd_bwd_nnz": flops_fwd_bwd(wl)},
+        "clocks": clocks,
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": gw_host.numel() * 8},
+        "gpu_launches": launches_per_step,
+        "roofline": roof,
+        "roofline_stages": stages,
+        "cpu_baseline": cpu,
+        "tflops_nnz": flops_fwd_bwd(wl) / (ms_dev * 1e-3) / 1e12,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sfno_block_721x1440x73", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="best", choices=["best", "fp32", "tf32"])
+    ap.add_argument("--act", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-stages", action="store_true", help="skip per-stage kernel timing")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
