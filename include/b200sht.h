@@ -129,7 +129,7 @@ int b200sht_sht_inverse_adjoint(const b200sht_plan* plan, const void* gy, int dt
 
 /* -------------------------------------------------------------------------------------- channel mix */
 /* weight re-layout: native torch parameter (complex64, shapes per b200sht_mix_op) -> packed
- * float [L][G][Ci/G][cop][2] (cop = Co/G rounded up to 2; l-stride 0 for OP_SHARED).  Only the dense
+ * float [L][G][Ci/G][2][cop] (real and imaginary planes; cop = Co/G rounded up to 4; l-stride 0 for OP_SHARED).  Only the dense
  * operators (DHCONV, SHARED, LDEP) use a packed weight; the others read the native layout. */
 int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co);
 int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, void* stream);

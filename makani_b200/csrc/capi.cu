@@ -269,7 +269,7 @@ int b200sht_sht_inverse_adjoint(const b200sht_plan* pl, const void* gy, int dtyp
 // --------------------------------------------------------------------------------------- channel mix
 int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co) {
   if (G <= 0 || Ci % G || Co % G) return -1;
-  const int64_t Cig = Ci / G, Cog = Co / G, cop = round_up((int)Cog, 2);
+  const int64_t Cig = Ci / G, Cog = Co / G, cop = round_up((int)Cog, 4);
   switch (op) {
     case B200SHT_OP_DHCONV: return (int64_t)L * G * Cig * cop * 2;
     case B200SHT_OP_LDEP: return (int64_t)L * Cig * cop * 2;

@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kFftThreads) fft_analysis_kernel(const T* __re
     float sc;
     if (prm.scale_mode == 0) sc = prm.rowscale[k];
     else sc = (m == 0 || 2 * m == N) ? 1.f : 2.f;
-    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = v * sc;
+    // rows in the k padding (k >= nlat) are written as exact zeros (pair splitting leaves rounding noise there)
+    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (k < prm.nlat) ? v * sc : 0.f;
   }
 }
 

@@ -13,14 +13,14 @@ namespace b200sht {
 struct MixDims {
   int L, M, B, G, Cig, Cog;   // per-group channel counts
   int cpi, cpo;               // padded total channel counts of the in / out spec tensors
-  int cop;                    // padded Cog in the packed weight
+  int cop;                    // padded Cog in the packed weight (planar: float [L][G][Cig][2][cop])
   long long wl_stride;        // floats between consecutive l in the packed weight (0: shared)
 };
 
 // ------------------------------------------------------------------------------------ weight re-layout
-// native DHCONV complex [G][Cig][Cog][L]  <->  packed float [L][G][Cig][cop][2]
-__global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(const float2* __restrict__ wn, float2* __restrict__ wp, int L, int GC /*G*Cig*/,
-                                                                 int Cog, int cop, int to_native) {
+// native DHCONV complex [G][Cig][Cog][L]  <->  packed float [L][G][Cig][2][cop]  (real plane, imaginary plane per input row)
+__global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restrict__ wn, float* __restrict__ wp, int L, int GC /*G*Cig*/, int Cog,
+                                                                 int cop, int to_native) {
   __shared__ float2 tile[32][33];
   const int gi = blockIdx.z;
   const int o0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
@@ -35,47 +35,58 @@ __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(const float2* _
     __syncthreads();
     for (int ll = ty; ll < 32; ll += 8) {
       const int l = l0 + ll, o = o0 + tx;
-      if (l < L && o < cop) wp[((size_t)l * GC + gi) * cop + o] = tile[tx][ll];
+      if (l < L && o < cop) {
+        float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
+        row[o] = tile[tx][ll].x;
+        row[cop + o] = tile[tx][ll].y;
+      }
     }
   } else {
     for (int ll = ty; ll < 32; ll += 8) {
       const int l = l0 + ll, o = o0 + tx;
       float2 v = make_float2(0.f, 0.f);
-      if (l < L && o < cop) v = wp[((size_t)l * GC + gi) * cop + o];
+      if (l < L && o < cop) {
+        const float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
+        v = make_float2(row[o], row[cop + o]);
+      }
       tile[tx][ll] = v;
     }
     __syncthreads();
     for (int oo = ty; oo < 32; oo += 8) {
       const int o = o0 + oo, l = l0 + tx;
-      if (o < Cog && l < L) const_cast<float2*>(wn)[((size_t)gi * Cog + o) * L + l] = tile[oo][tx];
+      if (o < Cog && l < L) wn[((size_t)gi * Cog + o) * L + l] = tile[oo][tx];
     }
   }
 }
 
-// native [rows][Co] complex <-> packed [rows][cop][2]   (OP_SHARED: rows = Ci, OP_LDEP: rows = L*Ci)
-__global__ void weight_pad_kernel(const float2* __restrict__ wn, float2* __restrict__ wp, long long rows, int Co, int cop, int to_native) {
+// native [rows][Co] complex <-> packed [rows][2][cop]   (OP_SHARED: rows = Ci, OP_LDEP: rows = L*Ci)
+__global__ void weight_pad_kernel(float2* __restrict__ wn, float* __restrict__ wp, long long rows, int Co, int cop, int to_native) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cop) return;
   const long long row = idx / cop;
   const int o = (int)(idx - row * cop);
-  if (!to_native) wp[idx] = (o < Co) ? wn[row * Co + o] : make_float2(0.f, 0.f);
-  else if (o < Co) const_cast<float2*>(wn)[row * Co + o] = wp[idx];
+  float* prow = wp + row * 2 * cop;
+  if (!to_native) {
+    const float2 v = (o < Co) ? wn[row * Co + o] : make_float2(0.f, 0.f);
+    prow[o] = v.x;
+    prow[cop + o] = v.y;
+  } else if (o < Co) {
+    wn[row * Co + o] = make_float2(prow[o], prow[cop + o]);
+  }
 }
 
 int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, cudaStream_t st) {
   B200_REQUIRE(G > 0 && Ci % G == 0 && Co % G == 0, "mix_weight: channels (%d,%d) not divisible by groups %d", Ci, Co, G);
-  const int Cig = Ci / G, Cog = Co / G, cop = round_up(Cog, 2);
+  const int Cig = Ci / G, Cog = Co / G, cop = round_up(Cog, 4);
   if (op == B200SHT_OP_DHCONV) {
     dim3 grid(ceil_div(L, 32), ceil_div(cop, 32), G * Cig);
     B200_REQUIRE(grid.z <= 65535, "mix_weight: G*Cig=%u exceeds grid limit", grid.z);
-    weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<const float2*>(w_native), reinterpret_cast<float2*>(w_packed), L, G * Cig, Cog,
-                                                   cop, to_native);
+    weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop, to_native);
   } else if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) {
     B200_REQUIRE(G == 1, "mix_weight: OP_SHARED/OP_LDEP are ungrouped");
     const long long rows = (op == B200SHT_OP_SHARED) ? Ci : (long long)L * Ci;
     const long long total = rows * cop;
-    weight_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<const float2*>(w_native), reinterpret_cast<float2*>(w_packed),
-                                                                      rows, Co, cop, to_native);
+    weight_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, rows, Co, cop, to_native);
   } else {
     set_error("mix_weight: operator %d has no packed weight", op);
     return B200SHT_ERR_INVALID;
@@ -134,17 +145,17 @@ __global__ void __launch_bounds__(256) mix_dense_kernel(const float* __restrict_
       wkk = t >> 4; woo = (t & 15) * 2;
       const int i = k0 + wkk, o = o0 + woo;
       if (i < K) {
-        const float* p = wl + ((size_t)(g * d.Cig + i) * d.cop + o) * 2;
-        if (o < d.Cog) { w0r = p[0]; w0i = p[1]; }
-        if (o + 1 < d.Cog) { w1r = p[2]; w1i = p[3]; }
+        const float* p = wl + (size_t)(g * d.Cig + i) * 2 * d.cop + o;
+        if (o < d.Cog) { w0r = p[0]; w0i = p[d.cop]; }
+        if (o + 1 < d.Cog) { w1r = p[1]; w1i = p[d.cop + 1]; }
       }
     } else {          // tile [kk = o][oo = i]: thread -> ii = t/8, kq = (t%8)*2
       woo = t >> 3; wkk = (t & 7) * 2;
       const int i = o0 + woo, o = k0 + wkk;
       if (i < d.Cig) {
-        const float* p = wl + ((size_t)(g * d.Cig + i) * d.cop + o) * 2;
-        if (o < K) { w0r = p[0]; w0i = p[1]; }
-        if (o + 1 < K) { w1r = p[2]; w1i = p[3]; }
+        const float* p = wl + (size_t)(g * d.Cig + i) * 2 * d.cop + o;
+        if (o < K) { w0r = p[0]; w0i = p[d.cop]; }
+        if (o + 1 < K) { w1r = p[1]; w1i = p[d.cop + 1]; }
       }
     }
     __syncthreads();
@@ -246,9 +257,9 @@ __global__ void __launch_bounds__(256) mix_wgrad_kernel(const float* __restrict_
     for (int c = 0; c < 2; ++c) {
       const int o = o0 + tx * 2 + c;
       if (o >= d.cop) continue;
-      float* p = gwl + ((size_t)(g * d.Cig + i) * d.cop + o) * 2;
+      float* p = gwl + (size_t)(g * d.Cig + i) * 2 * d.cop + o;
       p[0] = (o < d.Cog) ? ar[a][c] : 0.f;
-      p[1] = (o < d.Cog) ? ai[a][c] : 0.f;
+      p[d.cop] = (o < d.Cog) ? ai[a][c] : 0.f;
     }
   }
 }
@@ -275,6 +286,12 @@ __global__ void mix_cbias_grad_kernel(const float* __restrict__ gy, float2* __re
     for (int s = 16; s > 0; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); b2 += __shfl_xor_sync(0xffffffffu, b2, s); }
     if (threadIdx.x == 0) gcb[o] = make_float2(a, b2);
   }
+}
+
+int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, cudaStream_t st) {
+  mix_cbias_grad_kernel<<<Co, 256, 0, st>>>(gy, static_cast<float2*>(gcb), L, M, B, round_up(Co, 4));
+  B200_CHECK_LAUNCH();
+  return 0;
 }
 
 // ------------------------------------------------------------------------- per-mode (non-dense) operators
@@ -370,7 +387,7 @@ static int make_dims(const Plan* pl, int op, int B, int G, int Ci, int Co, MixDi
   if (op == B200SHT_OP_SEP_DHCONV || op == B200SHT_OP_SEP_DIAGONAL) B200_REQUIRE(Ci == Co, "mix: separable operator needs Ci == Co");
   if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) B200_REQUIRE(G == 1, "mix: OP_SHARED/OP_LDEP are ungrouped");
   d->L = pl->lmax; d->M = pl->mmax; d->B = B; d->G = G; d->Cig = Ci / G; d->Cog = Co / G;
-  d->cpi = round_up(Ci, 4); d->cpo = round_up(Co, 4); d->cop = round_up(Co / G, 2);
+  d->cpi = round_up(Ci, 4); d->cpo = round_up(Co, 4); d->cop = round_up(Co / G, 4);
   d->wl_stride = (op == B200SHT_OP_SHARED) ? 0 : (long long)G * (Ci / G) * d->cop * 2;
   return 0;
 }

@@ -1,12 +1,723 @@
-// tcgen05 / TMA path -- placeholder until the kernels land (phase B).  umma_plan_init() reports "unavailable" so that
-// every TF32 request fails loudly (b200sht_* returns B200SHT_ERR_UNSUPPORTED) instead of silently using another path.
+// tcgen05 / TMA path (B200SHT_PREC_TF32): the Legendre contractions and the dense channel mix as TMA-fed tensor-core
+// GEMMs with fp32 accumulators in TMEM.
+//
+//   one engine (umma_kernel<Traits>): 4 warps; warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer, all four
+//   warps = epilogue (warp w owns TMEM lanes 32w..32w+31).  smem ring of `stages` operand stages guarded by full/empty
+//   mbarriers; tcgen05.commit releases a stage and finally signals the epilogue.
+//
+//   five Traits supply the per-operation pieces (tile coordinates, TMA boxes, MMA issue list, epilogue):
+//     AnaTraits   spec[l][m][n]  = sum_k P[m][l][k] X[m][n][k]          A K-major,  B K-major     (RealSHT einsum "...km,mlk->...lm")
+//     SynTraits   Z[m][n][k]     = sum_l P[m][l][k] spec[l][m][n]       A MN-major, B MN-major    (InverseRealSHT "...lm,mlk->...km")
+//     MixFwd      y[row][o]      = sum_i x[row][i] w[i][o]   (complex)  A K-major,  B MN-major    (contractions.py:23 "bgixy,giox->bgoxy")
+//     MixDgrad    gx[row][i]     = sum_o gy[row][o] conj(w[i][o])       A K-major,  B K-major
+//     MixWgrad    gw[i][o]       = sum_row conj(x[row][i]) gy[row][o]   A MN-major, B MN-major
+//   complex products use planar operands: 4 real MMAs into two accumulators (real, imaginary), one of them with the
+//   instruction descriptor's negate-A bit.
+//
+// All shared-memory operand tiles use the 128-byte swizzle; every TMA box is [rows][32 floats] so it lands as rows of 128 B.
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
 namespace b200sht {
-int umma_plan_init(Plan* pl) { pl->umma_state = nullptr; return -1; }
+
+// =============================================================================================== PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done;
+}
+// bounded wait: a lost arrival traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("b200sht umma: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO (all >> 4), version = 1 (bit 46),
+// layout type SWIZZLE_128B = 2 (bits 61..63).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// K-major operand tile: rows of 128 B (32 floats of K), 8-row groups 1024 B apart.  kstep selects the K = 8 slice (32 B).
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) { return make_smem_desc(tile + kstep * 32, 16, 1024); }
+// MN-major operand tile: blocks of [32 K-rows][32 floats of M/N]; blocks `blk_bytes` apart; kstep selects 8 K-rows (1024 B).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep, uint32_t blk_bytes) {
+  return make_smem_desc(tile + kstep * 1024, blk_bytes, 1024);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32, fp32 accumulate, M = 128.
+__host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major, int negate_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)negate_a << 13) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ======================================================================================================= engine
+constexpr int kUmmaThreads = 128;
+constexpr int kMaxStages = 8;
+
+template <class T>
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ typename T::Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  typename T::Tile tile;
+  if (!T::make_tile(p, tile)) return;  // uniform per CTA
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int stages = p.stages;
+  const uint32_t stage_bytes = p.stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* accum = empty + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+    T::prefetch(p);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nk = T::num_kblocks(p, tile);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % stages, it = kb / stages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        mbar_expect_tx(&full[s], p.tx_bytes);
+        T::load(p, tile, kb, base + s * stage_bytes, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % stages, it = kb / stages;
+        mbar_wait(&full[s], it & 1);
+        tc_fence_after();
+        T::mma(p, tile, base + s * stage_bytes, tmem, kb > 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+    __syncwarp();
+  }
+  mbar_wait(accum, 0);
+  tc_fence_after();
+  T::epilogue(p, tile, tmem, warp, lane, nk);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+struct EngineParams {
+  int stages;
+  uint32_t stage_bytes, tx_bytes, tmem_cols;
+};
+
+// ================================================================================================ AnaTraits
+struct AnaTraits {
+  struct Params : EngineParams {
+    alignas(64) CUtensorMap tmA;  // table  (k, l, m)       box (32, 128, 1)
+    alignas(64) CUtensorMap tmB;  // X      (k, c, pb, m)   box (32, Cc, PBc, 1)
+    float* spec;
+    int L, M, nlat, C, cp, PB, Cc, PBc, n_ct, N;
+    uint32_t idesc;
+  };
+  struct Tile { int m, l0, c0, pb0; };
+  __device__ static bool make_tile(const Params& p, Tile& t) {
+    t.m = blockIdx.z;
+    t.l0 = lstart(t.m) + 128 * blockIdx.x;
+    t.c0 = (blockIdx.y % p.n_ct) * p.Cc;
+    t.pb0 = (blockIdx.y / p.n_ct) * p.PBc;
+    return t.l0 < p.L;
+  }
+  __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
+  __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.nlat + 31) / 32; }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    tma_load_3d(st, &p.tmA, bar, kb * 32, t.l0, t.m);
+    tma_load_4d(st + 16384, &p.tmB, bar, kb * 32, t.c0, t.pb0, t.m);
+  }
+  __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) umma_tf32(tmem, desc_kmajor(st, j), desc_kmajor(st + 16384, j), p.idesc, (acc || j > 0) ? 1u : 0u);
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk) {
+    const int l = t.l0 + warp * 32 + lane;
+    const int ncols = p.Cc * p.PBc;
+    const size_t JP = (size_t)p.PB * p.cp;
+    float* orow = p.spec + ((size_t)(l < p.L ? l : 0) * p.M + t.m) * JP;
+    float v[32];
+    for (int n0 = 0; n0 < ncols; n0 += 32) {
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, v);
+      if (l >= p.L) continue;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int n = n0 + q * 4;
+        if (n >= ncols) break;
+        const int pbi = n / p.Cc, ci = n - pbi * p.Cc;
+        const int pb = t.pb0 + pbi, c = t.c0 + ci;
+        if (pb < p.PB && c < p.cp) *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+  }
+};
+
+// ================================================================================================ SynTraits
+struct SynTraits {
+  struct Params : EngineParams {
+    alignas(64) CUtensorMap tmA;  // table (k, l, m)   box (32, 32, 1)   MN-major A (M = k)
+    alignas(64) CUtensorMap tmB;  // spec  (n, m, l)   box (32, 1, 32)   MN-major B (N = n)
+    float* Z;
+    int L, M, nlat, kp, C, cp, PB, nblk, N;
+    uint32_t idesc;
+  };
+  struct Tile { int m, k0, n0, lbeg; };
+  __device__ static bool make_tile(const Params& p, Tile& t) {
+    t.m = blockIdx.z;
+    t.k0 = 128 * blockIdx.x;
+    t.n0 = p.N * blockIdx.y;
+    t.lbeg = lstart(t.m);
+    return true;
+  }
+  __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
+  __device__ static int num_kblocks(const Params& p, const Tile& t) { return (p.L - t.lbeg + 31) / 32; }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    const int l = t.lbeg + kb * 32;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) tma_load_3d(st + b * 4096, &p.tmA, bar, t.k0 + 32 * b, l, t.m);
+    for (int b = 0; b < p.nblk; ++b) tma_load_3d(st + 16384 + b * 4096, &p.tmB, bar, t.n0 + 32 * b, t.m, l);
+  }
+  __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      umma_tf32(tmem, desc_mnmajor(st, j, 4096), desc_mnmajor(st + 16384, j, 4096), p.idesc, (acc || j > 0) ? 1u : 0u);
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk) {
+    const int k = t.k0 + warp * 32 + lane;
+    const int JP = p.PB * p.cp;
+    float v[32];
+    for (int n0 = 0; n0 < p.N; n0 += 32) {
+      if (t.n0 + n0 >= JP) break;
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, v);
+      if (k >= p.kp) continue;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int jp = t.n0 + n0 + q;
+        if (jp >= JP) break;
+        const int pb = jp / p.cp, c = jp - pb * p.cp;
+        if (c < p.C) p.Z[(((size_t)t.m * p.PB + pb) * p.C + c) * p.kp + k] = (nk > 0) ? v[q] : 0.f;
+      }
+    }
+  }
+};
+
+// ====================================================================================================== mix
+// spec tensor map: dims (c, b, p, m, l) with strides (1, cp, B*cp, 2*B*cp, M*2*B*cp) floats.
+// weight tensor map (planar packed weight [Lw][G][Cig][2][cop]): dims (o, p, i, lg) strides (1, cop, 2*cop, Cig*2*cop).
+struct MixParams : EngineParams {
+  alignas(64) CUtensorMap tmX;   // operand read as rows (m, b)
+  alignas(64) CUtensorMap tmX2;  // second spec operand (wgrad: gy)
+  alignas(64) CUtensorMap tmW;
+  float* out;              // spec (fwd / dgrad) or packed weight gradient (wgrad)
+  const float2* cbias;
+  int L, M, B, G, Cig, Cog, cpi, cpo, cop;
+  int Mt;                  // m values per row tile (Mt * B <= 128 rows)
+  int nblk, N;             // N = output columns per tile; nblk = N / 32 (MN-major B operands)
+  int n_nt;                // output tiles per group
+  int shared_w;            // weight has no l dimension
+  long long wl_stride;
+  uint32_t idesc, idesc_neg;
+  uint32_t offA_i, offB_r, offB_i;  // stage offsets of the imaginary A tile and the two B tiles (A_r at 0)
+};
+
+struct MixFwdTraits {
+  using Params = MixParams;
+  struct Tile { int l, m0, g, o0, lg; };
+  __device__ static bool make_tile(const Params& p, Tile& t) {
+    t.l = blockIdx.z;
+    t.m0 = blockIdx.x * p.Mt;
+    t.g = blockIdx.y / p.n_nt;
+    t.o0 = (blockIdx.y % p.n_nt) * p.N;
+    t.lg = (p.shared_w ? 0 : t.l * p.G) + t.g;
+    return t.m0 < mend(t.l, p.M);
+  }
+  __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmW); }
+  __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.Cig + 31) / 32; }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    const int c = t.g * p.Cig + kb * 32;
+    tma_load_5d(st, &p.tmX, bar, c, 0, 0, t.m0, t.l);
+    tma_load_5d(st + p.offA_i, &p.tmX, bar, c, 0, 1, t.m0, t.l);
+    for (int b = 0; b < p.nblk; ++b) {
+      tma_load_4d(st + p.offB_r + b * 4096, &p.tmW, bar, t.o0 + 32 * b, 0, kb * 32, t.lg);
+      tma_load_4d(st + p.offB_i + b * 4096, &p.tmW, bar, t.o0 + 32 * b, 1, kb * 32, t.lg);
+    }
+  }
+  __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t ar = desc_kmajor(st, j), ai = desc_kmajor(st + p.offA_i, j);
+      const uint64_t br = desc_mnmajor(st + p.offB_r, j, 4096), bi = desc_mnmajor(st + p.offB_i, j, 4096);
+      const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
+      umma_tf32(tmem, ar, br, p.idesc, a0);            // yr  = xr wr
+      umma_tf32(tmem, ai, bi, p.idesc_neg, 1u);        // yr -= xi wi
+      umma_tf32(tmem + p.N, ar, bi, p.idesc, a0);      // yi  = xr wi
+      umma_tf32(tmem + p.N, ai, br, p.idesc, 1u);      // yi += xi wr
+    }
+  }
+  // rows (mi, b) -> spec rows; columns -> output channels of group g; handles cbias and the zero channel padding
+  __device__ static void store_rows(const Params& p, int l, int m0, int g, int o0, int NOg, int cp_out, uint32_t tmem, int warp, int lane,
+                                    bool with_bias) {
+    const int r = warp * 32 + lane;
+    const int m = m0 + r / p.B, b = r % p.B;
+    const bool row_ok = (r < p.Mt * p.B) && (m < mend(l, p.M));
+    const int pad = cp_out - NOg * p.G;
+    const int limit = NOg + ((g == p.G - 1) ? pad : 0);  // columns of this group incl. trailing zero padding
+    float* yr = p.out + ((size_t)(row_ok ? l : 0) * p.M + (row_ok ? m : 0)) * 2 * p.B * cp_out + (size_t)b * cp_out + g * NOg;
+    float* yi = yr + (size_t)p.B * cp_out;
+    float vr[32], vi[32];
+    for (int n0 = 0; n0 < p.N; n0 += 32) {
+      if (o0 + n0 >= limit) break;
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, vr);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.N + n0, vi);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int o = o0 + n0 + q;
+        if (o >= limit) break;
+        float a = vr[q], c = vi[q];
+        if (o >= NOg) { a = 0.f; c = 0.f; }
+        else if (with_bias) { const float2 cb = p.cbias[g * NOg + o]; a += cb.x; c += cb.y; }
+        yr[o] = a;
+        yi[o] = c;
+      }
+    }
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk) {
+    store_rows(p, t.l, t.m0, t.g, t.o0, p.Cog, p.cpo, tmem, warp, lane, p.cbias != nullptr);
+  }
+};
+
+struct MixDgradTraits {
+  using Params = MixParams;   // tmX = gy (channels = Cout), out = gx; N tiles over i
+  using Tile = MixFwdTraits::Tile;  // o0 is the first input channel i0 of the tile
+  __device__ static bool make_tile(const Params& p, Tile& t) { return MixFwdTraits::make_tile(p, t); }
+  __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmW); }
+  __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.Cog + 31) / 32; }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    const int c = t.g * p.Cog + kb * 32;
+    tma_load_5d(st, &p.tmX, bar, c, 0, 0, t.m0, t.l);
+    tma_load_5d(st + p.offA_i, &p.tmX, bar, c, 0, 1, t.m0, t.l);
+    tma_load_4d(st + p.offB_r, &p.tmW, bar, kb * 32, 0, t.o0, t.lg);   // box (32 o, 1, N i, 1): K-major rows i
+    tma_load_4d(st + p.offB_i, &p.tmW, bar, kb * 32, 1, t.o0, t.lg);
+  }
+  __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t ar = desc_kmajor(st, j), ai = desc_kmajor(st + p.offA_i, j);
+      const uint64_t br = desc_kmajor(st + p.offB_r, j), bi = desc_kmajor(st + p.offB_i, j);
+      const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
+      umma_tf32(tmem, ar, br, p.idesc, a0);            // gxr  = gr wr
+      umma_tf32(tmem, ai, bi, p.idesc, 1u);            // gxr += gi wi
+      umma_tf32(tmem + p.N, ai, br, p.idesc, a0);      // gxi  = gi wr
+      umma_tf32(tmem + p.N, ar, bi, p.idesc_neg, 1u);  // gxi -= gr wi
+    }
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk) {
+    MixFwdTraits::store_rows(p, t.l, t.m0, t.g, t.o0, p.Cig, p.cpi, tmem, warp, lane, false);
+  }
+};
+
+struct MixWgradTraits {
+  using Params = MixParams;   // tmX = x (A, rows i), tmX2 = gy (B, cols o); K = spectral rows (m, b)
+  struct Tile { int lz, i0, g, o0; };
+  __device__ static bool make_tile(const Params& p, Tile& t) {
+    t.lz = blockIdx.z;
+    t.i0 = blockIdx.x * 128;
+    t.g = blockIdx.y / p.n_nt;
+    t.o0 = (blockIdx.y % p.n_nt) * p.N;
+    return true;
+  }
+  __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmX2); }
+  __device__ static int kb_of_l(const Params& p, int l) { return (mend(l, p.M) * p.B + 31) / 32; }
+  __device__ static int num_kblocks(const Params& p, const Tile& t) {
+    if (!p.shared_w) return kb_of_l(p, t.lz);
+    int n = 0;
+    for (int l = 0; l < p.L; ++l) n += kb_of_l(p, l);
+    return n;
+  }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    int l = t.lz;
+    if (p.shared_w) {
+      l = 0;
+      int n = kb_of_l(p, 0);
+      while (kb >= n) { kb -= n; ++l; n = kb_of_l(p, l); }
+    }
+    const int m = kb * (32 / p.B);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      tma_load_5d(st + a * 4096, &p.tmX, bar, t.g * p.Cig + t.i0 + 32 * a, 0, 0, m, l);
+      tma_load_5d(st + p.offA_i + a * 4096, &p.tmX, bar, t.g * p.Cig + t.i0 + 32 * a, 0, 1, m, l);
+    }
+    for (int b = 0; b < p.nblk; ++b) {
+      tma_load_5d(st + p.offB_r + b * 4096, &p.tmX2, bar, t.g * p.Cog + t.o0 + 32 * b, 0, 0, m, l);
+      tma_load_5d(st + p.offB_i + b * 4096, &p.tmX2, bar, t.g * p.Cog + t.o0 + 32 * b, 0, 1, m, l);
+    }
+  }
+  __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t ar = desc_mnmajor(st, j, 4096), ai = desc_mnmajor(st + p.offA_i, j, 4096);
+      const uint64_t br = desc_mnmajor(st + p.offB_r, j, 4096), bi = desc_mnmajor(st + p.offB_i, j, 4096);
+      const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
+      umma_tf32(tmem, ar, br, p.idesc, a0);            // gwr  = xr gr
+      umma_tf32(tmem, ai, bi, p.idesc, 1u);            // gwr += xi gi
+      umma_tf32(tmem + p.N, ar, bi, p.idesc, a0);      // gwi  = xr gi
+      umma_tf32(tmem + p.N, ai, br, p.idesc_neg, 1u);  // gwi -= xi gr
+    }
+  }
+  __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk) {
+    const int i = t.i0 + warp * 32 + lane;
+    const bool ok = i < p.Cig;
+    float* row = p.out + (size_t)(p.shared_w ? 0 : t.lz) * p.wl_stride + (size_t)(t.g * p.Cig + (ok ? i : 0)) * 2 * p.cop;
+    float vr[32], vi[32];
+    for (int n0 = 0; n0 < p.N; n0 += 32) {
+      if (t.o0 + n0 >= p.cop) break;
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, vr);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.N + n0, vi);
+      if (!ok) continue;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int o = t.o0 + n0 + q;
+        if (o >= p.cop) break;
+        row[o] = (o < p.Cog) ? vr[q] : 0.f;
+        row[p.cop + o] = (o < p.Cog) ? vi[q] : 0.f;
+      }
+    }
+  }
+};
+
+// ================================================================================================== host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+// fp32 tensor map, 128-byte swizzle.  dims[0] is the contiguous dimension; strides (in floats) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides, const int* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }
+  for (int i = 1; i < rank; ++i) {
+    gs[i - 1] = (cuuint64_t)strides[i] * 4;
+    if (gs[i - 1] % 16 != 0) { set_error("tensor map stride %lld floats is not 16-byte aligned", strides[i]); return B200SHT_ERR_INVALID; }
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { set_error("tensor map base is not 16-byte aligned"); return B200SHT_ERR_INVALID; }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return B200SHT_ERR_CUDA; }
+  return 0;
+}
+
+static int g_umma_ok = -1;
+int umma_available() {
+  if (g_umma_ok >= 0) return g_umma_ok;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  g_umma_ok = (major == 10 && get_encode() != nullptr) ? 1 : 0;
+  return g_umma_ok;
+}
+
+int umma_plan_init(Plan* pl) {
+  pl->umma_state = nullptr;
+  return umma_available() ? 0 : -1;
+}
 void umma_plan_destroy(Plan*) {}
-int umma_available() { return 0; }
-int legendre_analysis_umma(const Plan*, const float*, float*, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return B200SHT_ERR_UNSUPPORTED; }
-int legendre_synthesis_umma(const Plan*, const float*, float*, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return B200SHT_ERR_UNSUPPORTED; }
-int mix_forward_umma(const Plan*, int, const float*, const void*, const void*, float*, int, int, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return B200SHT_ERR_UNSUPPORTED; }
-int mix_backward_umma(const Plan*, int, const float*, const void*, const float*, float*, void*, void*, int, int, int, int, cudaStream_t) { set_error("tcgen05 path not built"); return B200SHT_ERR_UNSUPPORTED; }
+
+constexpr size_t kSmemMax = 232448 - 2048;  // 227 KB minus barriers / alignment slack
+
+static void pick_stages(EngineParams* e, uint32_t stage_bytes, int max_useful) {
+  e->stage_bytes = stage_bytes;
+  size_t budget = (3ull * stage_bytes <= 110 * 1024) ? 110 * 1024 : kSmemMax;  // two CTAs per SM when three stages fit in half
+  int s = (int)(budget / stage_bytes);
+  if (s > kMaxStages) s = kMaxStages;
+  if (s > max_useful) s = max_useful;
+  if (s < 2) s = 2;
+  e->stages = s;
+}
+static size_t smem_bytes(const EngineParams& e) { return (size_t)e.stages * e.stage_bytes + 1024 /*align*/ + (2 * kMaxStages + 2) * 8 + 16; }
+static uint32_t tmem_cols_pow2(int cols) { uint32_t c = 32; while ((int)c < cols) c <<= 1; return c; }
+
+template <class T>
+static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
+  const size_t smem = smem_bytes(p);
+  if (smem > 232448) { set_error("umma: %zu bytes of shared memory needed", smem); return B200SHT_ERR_UNSUPPORTED; }
+  B200_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_kernel<T><<<grid, kUmmaThreads, smem, st>>>(p);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- Legendre
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st) {
+  AnaTraits::Params p;
+  memset(&p, 0, sizeof(p));
+  const int cp = round_up(C, 4), PB = 2 * B;
+  p.spec = spec; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.C = C; p.cp = cp; p.PB = PB;
+  if (cp <= 128) { p.Cc = cp; p.n_ct = 1; p.PBc = 256 / cp < PB ? 256 / cp : PB; }
+  else { p.n_ct = ceil_div(cp, 128); p.Cc = round_up(ceil_div(cp, p.n_ct), 4); p.PBc = (2 * p.Cc <= 256 && PB >= 2) ? 2 : 1; }
+  const int rows = p.Cc * p.PBc;
+  p.N = round_up(rows, 16);
+  p.idesc = make_idesc(p.N, 0, 0, 0);
+  {
+    long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
+    int bx[3] = {32, 128, 1};
+    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx);
+    if (rc) return rc;
+  }
+  {
+    long long d[4] = {pl->nlat, C, PB, pl->mmax}, s[4] = {1, pl->kp, (long long)C * pl->kp, (long long)PB * C * pl->kp};
+    int bx[4] = {32, p.Cc, p.PBc, 1};
+    int rc = make_tmap(&p.tmB, X, 4, d, s, bx);
+    if (rc) return rc;
+  }
+  const uint32_t bbytes = (uint32_t)round_up(p.N * 128, 1024);
+  pick_stages(&p, 16384 + bbytes, ceil_div(pl->nlat, 32));
+  p.tx_bytes = 16384 + (uint32_t)rows * 128;
+  p.tmem_cols = tmem_cols_pow2(p.N);
+  dim3 grid(ceil_div(pl->lmax, 128), p.n_ct * ceil_div(PB, p.PBc), pl->mmax);
+  return launch<AnaTraits>(p, grid, st);
+}
+
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st) {
+  SynTraits::Params p;
+  memset(&p, 0, sizeof(p));
+  const int cp = round_up(C, 4), PB = 2 * B, JP = PB * cp;
+  p.Z = Z; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.kp = pl->kp; p.C = C; p.cp = cp; p.PB = PB;
+  p.nblk = ceil_div(JP, 32) < 8 ? ceil_div(JP, 32) : 8;
+  p.N = 32 * p.nblk;
+  p.idesc = make_idesc(p.N, 1, 1, 0);
+  {
+    long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
+    int bx[3] = {32, 32, 1};
+    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx);
+    if (rc) return rc;
+  }
+  {
+    long long d[3] = {JP, pl->mmax, pl->lmax}, s[3] = {1, JP, (long long)pl->mmax * JP};
+    int bx[3] = {32, 1, 32};
+    int rc = make_tmap(&p.tmB, spec, 3, d, s, bx);
+    if (rc) return rc;
+  }
+  pick_stages(&p, 16384 + 4096 * p.nblk, ceil_div(pl->lmax, 32));
+  p.tx_bytes = 16384 + 4096 * p.nblk;
+  p.tmem_cols = tmem_cols_pow2(p.N);
+  dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), pl->mmax);
+  return launch<SynTraits>(p, grid, st);
+}
+
+// --------------------------------------------------------------------------------------------------- mix
+static int spec_tmap(CUtensorMap* tm, const float* base, int L, int M, int B, int Ctot, int cp, int box_c, int box_b, int box_m) {
+  long long d[5] = {Ctot, B, 2, M, L};
+  long long s[5] = {1, cp, (long long)B * cp, 2ll * B * cp, (long long)M * 2 * B * cp};
+  int bx[5] = {box_c, box_b, 1, box_m, 1};
+  return make_tmap(tm, base, 5, d, s, bx);
+}
+static int weight_tmap(CUtensorMap* tm, const float* base, int Lw, int G, int Cig, int Cog, int cop, int box_o, int box_i) {
+  long long d[4] = {Cog, 2, Cig, (long long)Lw * G};
+  long long s[4] = {1, cop, 2ll * cop, (long long)Cig * 2 * cop};
+  int bx[4] = {box_o, 1, box_i, 1};
+  return make_tmap(tm, base, 4, d, s, bx);
+}
+
+static int fill_mix(const Plan* pl, int op, int B, int G, int Ci, int Co, MixParams* p) {
+  B200_REQUIRE(B >= 1 && 32 % B == 0, "tcgen05 mix: batch %d must divide 32 (use precision fp32 otherwise)", B);
+  memset(p, 0, sizeof(*p));
+  p->L = pl->lmax; p->M = pl->mmax; p->B = B; p->G = G; p->Cig = Ci / G; p->Cog = Co / G;
+  p->cpi = round_up(Ci, 4); p->cpo = round_up(Co, 4); p->cop = round_up(Co / G, 4);
+  p->shared_w = (op == B200SHT_OP_SHARED);
+  p->wl_stride = p->shared_w ? 0 : (long long)G * p->Cig * 2 * p->cop;
+  p->Mt = 128 / B;
+  return 0;
+}
+
+int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st) {
+  MixParams p;
+  int rc = fill_mix(pl, op, B, G, Ci, Co, &p);
+  if (rc) return rc;
+  p.out = y; p.cbias = static_cast<const float2*>(cbias);
+  const int cols = p.Cog + ((p.cpo - Co) > 0 ? (p.cpo - Co) : 0);   // last group's tile also writes the zero padding
+  p.nblk = ceil_div(cols, 32) < 8 ? ceil_div(cols, 32) : 8;
+  p.N = 32 * p.nblk;
+  p.n_nt = ceil_div(cols, p.N);
+  p.idesc = make_idesc(p.N, 0, 1, 0);
+  p.idesc_neg = make_idesc(p.N, 0, 1, 1);
+  p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;
+  rc = spec_tmap(&p.tmX, x, p.L, p.M, B, Ci, p.cpi, 32, B, p.Mt);
+  if (!rc) rc = weight_tmap(&p.tmW, static_cast<const float*>(w), p.shared_w ? 1 : p.L, G, p.Cig, p.Cog, p.cop, 32, 32);
+  if (rc) return rc;
+  pick_stages(&p, 32768 + 8192 * p.nblk, ceil_div(p.Cig, 32));
+  p.tx_bytes = 2u * (uint32_t)(p.Mt * B) * 128 + 8192u * p.nblk;
+  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  dim3 grid(ceil_div(p.M, p.Mt), p.n_nt * G, p.L);
+  return launch<MixFwdTraits>(p, grid, st);
+}
+
+int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
+                      int Ci, int Co, cudaStream_t st);
+
+int mix_dgrad_umma(const Plan* pl, int op, const void* w, const float* gy, float* gx, int B, int G, int Ci, int Co, cudaStream_t st) {
+  MixParams p;
+  int rc = fill_mix(pl, op, B, G, Ci, Co, &p);
+  if (rc) return rc;
+  p.out = gx;
+  const int cols = p.Cig + ((p.cpi - Ci) > 0 ? (p.cpi - Ci) : 0);
+  p.N = round_up(cols, 16) < 256 ? round_up(cols, 16) : 256;
+  p.n_nt = ceil_div(cols, p.N);
+  p.idesc = make_idesc(p.N, 0, 0, 0);
+  p.idesc_neg = make_idesc(p.N, 0, 0, 1);
+  const uint32_t bb = (uint32_t)round_up(p.N * 128, 1024);
+  p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + bb;
+  rc = spec_tmap(&p.tmX, gy, p.L, p.M, B, Co, p.cpo, 32, B, p.Mt);
+  if (!rc) rc = weight_tmap(&p.tmW, static_cast<const float*>(w), p.shared_w ? 1 : p.L, G, p.Cig, p.Cog, p.cop, 32, p.N);
+  if (rc) return rc;
+  pick_stages(&p, 32768 + 2 * bb, ceil_div(p.Cog, 32));
+  p.tx_bytes = 2u * (uint32_t)(p.Mt * B) * 128 + 2u * (uint32_t)p.N * 128;
+  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  dim3 grid(ceil_div(p.M, p.Mt), p.n_nt * G, p.L);
+  return launch<MixDgradTraits>(p, grid, st);
+}
+
+int mix_wgrad_umma(const Plan* pl, int op, const float* x, const float* gy, float* gw, int B, int G, int Ci, int Co, cudaStream_t st) {
+  MixParams p;
+  int rc = fill_mix(pl, op, B, G, Ci, Co, &p);
+  if (rc) return rc;
+  p.out = gw;
+  p.nblk = ceil_div(p.cop, 32) < 8 ? ceil_div(p.cop, 32) : 8;
+  p.N = 32 * p.nblk;
+  p.n_nt = ceil_div(p.cop, p.N);
+  p.idesc = make_idesc(p.N, 1, 1, 0);
+  p.idesc_neg = make_idesc(p.N, 1, 1, 1);
+  p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;
+  rc = spec_tmap(&p.tmX, x, p.L, p.M, B, Ci, p.cpi, 32, B, 32 / B);
+  if (!rc) rc = spec_tmap(&p.tmX2, gy, p.L, p.M, B, Co, p.cpo, 32, B, 32 / B);
+  if (rc) return rc;
+  pick_stages(&p, 32768 + 8192 * p.nblk, 8);
+  p.tx_bytes = 32768u + 8192u * p.nblk;
+  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  dim3 grid(ceil_div(p.Cig, 128), p.n_nt * G, p.shared_w ? 1 : p.L);
+  return launch<MixWgradTraits>(p, grid, st);
+}
+
+int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, cudaStream_t st);  // mix.cu
+
+int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
+                      int Ci, int Co, cudaStream_t st) {
+  int rc = 0;
+  if (gx) rc = mix_dgrad_umma(pl, op, w, gy, gx, B, G, Ci, Co, st);
+  if (!rc && gw) rc = mix_wgrad_umma(pl, op, x, gy, static_cast<float*>(gw), B, G, Ci, Co, st);
+  if (!rc && gcbias) rc = mix_cbias_grad(gy, gcbias, pl->lmax, pl->mmax, B, Co, st);
+  return rc;
+}
+
 }  // namespace b200sht

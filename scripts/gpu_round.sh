@@ -2,8 +2,13 @@
 # One GPU-box round trip: tests, smoke, bench; everything interesting lands in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q -rA -x --timeout=600 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
-echo "pytest exit: $?" >> gpurun_out/pytest_gpu.log
+timeout 900 python scripts/umma_diag.py all small odd tiles wide cfg2c > gpurun_out/umma_diag.log 2>&1
+echo "diag exit: $?" >> gpurun_out/umma_diag.log
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -rA --timeout=600 2>&1 | grep -E "parity\]|PASS|FAIL|ERROR|passed|failed|Error|assert" | tail -150 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests/test_gpu_umma.py -m gpu -q -rA --timeout=900 -k "not kernels_agree" 2>&1 | grep -E "parity\]|PASS|FAIL|ERROR|passed|failed|Error|assert" | tail -80 > gpurun_out/pytest_umma.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -60 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -5; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 600 python bench.py --steps 50 --warmup 5 --precision fp32 --no-cpu > gpurun_out/bench_fp32.json 2>> gpurun_out/bench.err
+echo "=== diag"; grep -E "^---|rel_l2|failures|!" gpurun_out/umma_diag.log | cut -c1-260 | tail -120
+echo "=== pytest"; tail -40 gpurun_out/pytest_gpu.log | cut -c1-200; echo "=== pytest umma"; tail -40 gpurun_out/pytest_umma.log | cut -c1-200
+echo "=== smoke"; tail -3 gpurun_out/smoke.log; echo "=== bench"; cat gpurun_out/bench.json | cut -c1-2500; tail -5 gpurun_out/bench.err
