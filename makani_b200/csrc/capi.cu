@@ -291,6 +291,11 @@ int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int
 }
 
 static bool dense_op(int op) { return op == B200SHT_OP_DHCONV || op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP; }
+// The tcgen05 mix addresses operands with TMA: group slices must start on 16-byte boundaries and the batch must divide 32.
+// Other shapes (none of the shipped configs: G = 1, B = 1 per GPU) are served by the fp32 CUDA-core kernels.
+static bool umma_mix_shape(int B, int G, int Ci, int Co) {
+  return B >= 1 && 32 % B == 0 && (G == 1 || ((Ci / G) % 4 == 0 && (Co / G) % 4 == 0));
+}
 
 int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co,
                         int precision, void* stream) {
@@ -299,7 +304,7 @@ int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, con
   if (rc) return rc;
   Plan p = lm_plan(L, M);
   const Plan* pl = &p;
-  if (precision == B200SHT_PREC_TF32 && dense_op(op)) return mix_forward_umma(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));
+  if (precision == B200SHT_PREC_TF32 && dense_op(op) && umma_mix_shape(B, G, Ci, Co)) return mix_forward_umma(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));
   return mix_forward_simt(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));  // per-mode operators are bandwidth bound: one path
 }
 
@@ -311,7 +316,7 @@ int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, co
   if (rc) return rc;
   Plan p = lm_plan(L, M);
   const Plan* pl = &p;
-  if (precision == B200SHT_PREC_TF32 && dense_op(op)) return mix_backward_umma(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
+  if (precision == B200SHT_PREC_TF32 && dense_op(op) && umma_mix_shape(B, G, Ci, Co)) return mix_backward_umma(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
   return mix_backward_simt(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
 }
 

@@ -2,45 +2,63 @@
 // InverseRealSHT; reference call sites /root/reference/makani/models/common/spectral_convolution.py:239,253 and
 // the FFT twin /root/reference/makani/mpu/fft.py:62,109).
 //
-// One CTA transforms KC = 2*PAIRS consecutive latitude rows of one (batch, channel) image: the rows are contiguous
-// in memory (coalesced, vectorised loads), two real rows are packed into one complex sequence, transformed with a
-// mixed-radix Stockham FFT in shared memory, split back into the two half spectra, truncated to mmax, scaled and
+// One CTA transforms KC = 2*PAIRS consecutive latitude rows of one (batch, channel) image: two real rows are packed
+// into one complex sequence, transformed with a mixed-radix Stockham FFT (radices up to 16 kept in registers, shared
+// memory only for the exchange between stages), split back into the two half spectra, truncated to mmax, scaled and
 // written in the "latspec" layout [m][re/im][row r][k] so that the KC results of one (m, re/im) form one contiguous
-// 32-byte sector and the Legendre GEMM can read K-major operands straight from it.
+// 32-byte sector and the Legendre GEMM reads K-major operands straight from it.
+//
+// Two kernel families share the butterflies:
+//   *_ct  : radix plan fixed at compile time (lengths 64 ... 2880 listed in CT_PLANS): all index arithmetic folds to
+//           constants, first stage fused with the global load, last stage of the inverse fused with the store,
+//           shared-memory indices skewed by i / R0 to spread the stride-R0 writes of the first stage over the banks.
+//   *_rt  : any length whose prime factors are <= 13 (runtime plan).
 //
 // The stage / butterfly code is __host__ __device__ so that the same arithmetic is unit-tested on the CPU
 // (b200sht_debug_fft_host) without a GPU.
 #include "common.cuh"
+#include "fft_roots.cuh"
 #include <cmath>
 #include <vector>
 
 namespace b200sht {
 
 // ------------------------------------------------------------------------------------------------ plan
+static const int kRadices[] = {16, 15, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+
+static void plan_search(int n, int max_r, int* cur, int depth, int* best, int* best_len, int* best_sum) {
+  if (n == 1) {
+    int sum = 0;
+    for (int i = 0; i < depth; ++i) sum += cur[i];
+    if (depth < *best_len || (depth == *best_len && sum < *best_sum)) {
+      *best_len = depth; *best_sum = sum;
+      for (int i = 0; i < depth; ++i) best[i] = cur[i];
+    }
+    return;
+  }
+  if (depth >= 12 || depth + 1 > *best_len) return;
+  for (int r : kRadices) {
+    if (r > max_r || n % r) continue;
+    cur[depth] = r;
+    plan_search(n / r, r, cur, depth + 1, best, best_len, best_sum);
+  }
+}
+
+// fewest stages, then smallest radix sum (balanced stages); radices in non-increasing order
 bool make_fft_plan(int N, FftPlan* p) {
   p->N = N;
   p->nstages = 0;
   if (N < 2) return false;
   int n = N;
-  int twos = 0;
-  while (n % 2 == 0) { n /= 2; ++twos; }
-  const int odd[] = {3, 5, 7, 11, 13};
-  int tmp[20];
-  int cnt = 0;
-  for (int r : odd)
-    while (n % r == 0) { n /= r; if (cnt >= 16) return false; tmp[cnt++] = r; }
+  for (int f : {2, 3, 5, 7, 11, 13})
+    while (n % f == 0) n /= f;
   if (n != 1) return false;
-  // powers of two: as many radix-8 as possible, remainder as 4 or 2 (4*4 preferred over 8*2)
-  int e8 = twos / 3, rem = twos % 3;
-  int e4 = 0, e2 = 0;
-  if (rem == 1) { if (e8 >= 1) { e8 -= 1; e4 = 2; } else e2 = 1; }
-  if (rem == 2) e4 += 1;
-  // small radices first (keeps Ns small while strides are large), odd ones last
-  for (int i = 0; i < e2; ++i) p->radix[p->nstages++] = 2;
-  for (int i = 0; i < e4; ++i) p->radix[p->nstages++] = 4;
-  for (int i = 0; i < e8; ++i) p->radix[p->nstages++] = 8;
-  for (int i = 0; i < cnt; ++i) p->radix[p->nstages++] = tmp[i];
-  return p->nstages <= 20;
+  int cur[20], best[20], best_len = 13, best_sum = 1 << 30;
+  plan_search(N, 16, cur, 0, best, &best_len, &best_sum);
+  if (best_len > 12) return false;
+  p->nstages = best_len;
+  for (int i = 0; i < best_len; ++i) p->radix[i] = best[i];
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------ butterflies
@@ -48,7 +66,6 @@ HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 HD float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
-HD float2 cmul_pi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
 
 template <int R>
 struct Butterfly;
@@ -144,7 +161,40 @@ struct Butterfly {
   }
 };
 
-// One Stockham butterfly (index j of N/R) of a stage with sub-transform length Ns:  in -> out.
+// Cooley-Tukey composite in registers: R = R1 * R2, input index n = R2 n1 + n2, output index k = k1 + R1 k2.
+template <int R1, int R2>
+struct Composite {
+  HD static void run(float2* v) {
+    constexpr int R = R1 * R2;
+    float2 t[R];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+      float2 u[R1];
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) u[n1] = v[R2 * n1 + n2];
+      Butterfly<R1>::run(u, nullptr, 0);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) t[n2 * R1 + k1] = (n2 * k1 == 0) ? u[k1] : cmul(u[k1], unit_root<R>(n2 * k1));
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      float2 u[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) u[n2] = t[n2 * R1 + k1];
+      Butterfly<R2>::run(u, nullptr, 0);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = u[k2];
+    }
+  }
+};
+template <> struct Butterfly<6> { HD static void run(float2* v, const float2*, int) { Composite<2, 3>::run(v); } };
+template <> struct Butterfly<9> { HD static void run(float2* v, const float2*, int) { Composite<3, 3>::run(v); } };
+template <> struct Butterfly<10> { HD static void run(float2* v, const float2*, int) { Composite<2, 5>::run(v); } };
+template <> struct Butterfly<12> { HD static void run(float2* v, const float2*, int) { Composite<4, 3>::run(v); } };
+template <> struct Butterfly<15> { HD static void run(float2* v, const float2*, int) { Composite<3, 5>::run(v); } };
+template <> struct Butterfly<16> { HD static void run(float2* v, const float2*, int) { Composite<4, 4>::run(v); } };
+
+// One Stockham butterfly (index j of N/R) of a stage with sub-transform length Ns:  in -> out  (runtime plan / host)
 template <int R>
 HD void stage_butterfly(const float2* in, float2* out, const float2* tw, int N, int Ns, int j) {
   const int k = j % Ns;
@@ -163,49 +213,28 @@ HD void stage_butterfly(const float2* in, float2* out, const float2* tw, int N, 
   for (int r = 0; r < R; ++r) out[j0 + r * Ns] = v[r];
 }
 
+#define B200_RADIX_SWITCH(R, CALL)      \
+  switch (R) {                          \
+    case 2: { CALL(2); } break;         \
+    case 3: { CALL(3); } break;         \
+    case 4: { CALL(4); } break;         \
+    case 5: { CALL(5); } break;         \
+    case 6: { CALL(6); } break;         \
+    case 7: { CALL(7); } break;         \
+    case 8: { CALL(8); } break;         \
+    case 9: { CALL(9); } break;         \
+    case 10: { CALL(10); } break;       \
+    case 11: { CALL(11); } break;       \
+    case 12: { CALL(12); } break;       \
+    case 13: { CALL(13); } break;       \
+    case 15: { CALL(15); } break;       \
+    default: { CALL(16); } break;       \
+  }
+
 // split the FFT of z = a + i b (a, b real rows) into the half spectra of a and b at mode m
 HD void split_pair(float2 Z, float2 Zm /* = FFT(z)[(N-m)%N] */, float2& A, float2& Bq) {
   A = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
   Bq = make_float2(0.5f * (Z.y + Zm.y), -0.5f * (Z.x - Zm.x));
-}
-
-// ------------------------------------------------------------------------------------------- kernels
-constexpr int kFftThreads = 256;
-
-template <int R>
-__device__ __forceinline__ void run_stage(const float2* in, float2* out, const float2* tw, int N, int Ns, int pairs,
-                                          int bufstride) {
-  const int nb = N / R;
-  for (int w = threadIdx.x; w < pairs * nb; w += kFftThreads) {
-    const int q = w / nb, j = w - q * nb;
-    stage_butterfly<R>(in + q * bufstride, out + q * bufstride, tw, N, Ns, j);
-  }
-}
-
-// runs all stages; returns pointer to the buffer holding the result
-__device__ __forceinline__ float2* run_fft(float2* b0, float2* b1, const float2* tw, const FftPlan& fp, int pairs,
-                                           int bufstride) {
-  float2* in = b0;
-  float2* out = b1;
-  int Ns = 1;
-  const int N = fp.N;
-  for (int s = 0; s < fp.nstages; ++s) {
-    const int R = fp.radix[s];
-    switch (R) {
-      case 2: run_stage<2>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 3: run_stage<3>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 4: run_stage<4>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 5: run_stage<5>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 7: run_stage<7>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 8: run_stage<8>(in, out, tw, N, Ns, pairs, bufstride); break;
-      case 11: run_stage<11>(in, out, tw, N, Ns, pairs, bufstride); break;
-      default: run_stage<13>(in, out, tw, N, Ns, pairs, bufstride); break;
-    }
-    Ns *= R;
-    __syncthreads();
-    float2* t = in; in = out; out = t;
-  }
-  return in;
 }
 
 struct FftParams {
@@ -219,116 +248,123 @@ struct FftParams {
   const float* bias;
 };
 
-__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]
-template <typename T, int PAIRS>
-__global__ void __launch_bounds__(kFftThreads) fft_analysis_kernel(const T* __restrict__ x, float* __restrict__ X,
-                                                                   const FftParams prm) {
+__device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m, int k) {
+  if (k >= prm.nlat) return 0.f;  // rows in the k padding are written as exact zeros
+  if (prm.scale_mode == 0) return prm.rowscale[k];
+  return (m == 0 || 2 * m == prm.nlon) ? 1.f : 2.f;
+}
+
+// =========================================================================================== compile-time plans
+template <int R0>
+__host__ __device__ constexpr int skew(int i) { return i + i / R0; }
+
+// stage s of a compile-time plan: smem (skewed) -> smem (skewed)
+template <int N, int R, int Ns, int R0, int THREADS>
+__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int pairs, int bufstride) {
+  constexpr int NB = N / R;
+  for (int w = threadIdx.x; w < pairs * NB; w += THREADS) {
+    const int q = w / NB, j = w - q * NB;
+    const int k = j % Ns;
+    const int tstep = k * (N / (Ns * R));
+    const float2* src = in + q * bufstride;
+    float2* dst = out + q * bufstride;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 a = src[skew<R0>(j + r * NB)];
+      if (Ns > 1 && r > 0) a = cmul(a, tw[r * tstep]);
+      v[r] = a;
+    }
+    Butterfly<R>::run(v, tw, N);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[skew<R0>(j0 + r * Ns)] = v[r];
+  }
+}
+
+template <int N, int R0>
+__host__ __device__ constexpr int ct_bufstride() { return (skew<R0>(N) + 2) | 1; }  // odd stride: the 4 pairs land on different banks
+
+// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2), R2 == 1 for two stages
+template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
+__global__ void __launch_bounds__(THREADS) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
+  constexpr int N = R0 * R1 * R2;
+  constexpr int BS = ct_bufstride<N, R0>();
+  constexpr int KC = 2 * PAIRS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = prm.nlon;
-  const int NS = N + 1;  // padded per-pair stride (float2 units)
   float2* tw = reinterpret_cast<float2*>(smem_raw);
   float2* b0 = tw + N;
-  float2* b1 = b0 + PAIRS * NS;
-  constexpr int KC = 2 * PAIRS;
+  float2* b1 = b0 + PAIRS * BS;
   const int k0 = blockIdx.x * KC;
   const int r = blockIdx.y;
+  for (int t = threadIdx.x; t < N; t += THREADS) tw[t] = prm.twiddle[t];
 
-  for (int t = threadIdx.x; t < N; t += kFftThreads) tw[t] = prm.twiddle[t];
-
-  // ---- load KC rows (contiguous in memory), packing row pairs into complex sequences
+  // ---- stage 0 fused with the global load: thread j of pair q reads elements j + r * N/R0 of rows k0+2q, k0+2q+1
   {
-    float* bf = reinterpret_cast<float*>(b0);
+    constexpr int NB = N / R0;
     const T* base = x + ((size_t)r * prm.nlat + k0) * N;
-    const int rows_valid = min(KC, prm.nlat - k0);
-    constexpr int V = 16 / sizeof(T);
-    const bool vec_ok = (N % V == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-    if (vec_ok) {
-      const int nv = N / V;
-      for (int e = threadIdx.x; e < KC * nv; e += kFftThreads) {
-        const int kk = e / nv, jv = e - kk * nv;
-        float vals[V];
-        if (kk < rows_valid) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)kk * N) + jv);
-          const T* pv = reinterpret_cast<const T*>(&raw);
+    for (int w = threadIdx.x; w < PAIRS * NB; w += THREADS) {
+      const int q = w / NB, j = w - q * NB;
+      const bool va = (k0 + 2 * q) < prm.nlat, vb = (k0 + 2 * q + 1) < prm.nlat;
+      const T* ra = base + (size_t)(2 * q) * N + j;
+      const T* rb = ra + N;
+      float2 v[R0];
 #pragma unroll
-          for (int i = 0; i < V; ++i) vals[i] = ld_as_float(pv + i);
-        } else {
+      for (int rr = 0; rr < R0; ++rr) v[rr] = make_float2(va ? ld_as_float(ra + rr * NB) : 0.f, vb ? ld_as_float(rb + rr * NB) : 0.f);
+      Butterfly<R0>::run(v, nullptr, N);
+      float2* dst = b0 + q * BS;
 #pragma unroll
-          for (int i = 0; i < V; ++i) vals[i] = 0.f;
-        }
-        float* dst = bf + ((size_t)(kk >> 1) * NS + jv * V) * 2 + (kk & 1);
-#pragma unroll
-        for (int i = 0; i < V; ++i) dst[2 * i] = vals[i];
-      }
-    } else {
-      for (int e = threadIdx.x; e < KC * N; e += kFftThreads) {
-        const int kk = e / N, j = e - kk * N;
-        const float v = (kk < rows_valid) ? ld_as_float(base + (size_t)kk * N + j) : 0.f;
-        bf[((size_t)(kk >> 1) * NS + j) * 2 + (kk & 1)] = v;
-      }
+      for (int rr = 0; rr < R0; ++rr) dst[skew<R0>(j * R0 + rr)] = v[rr];
     }
   }
   __syncthreads();
-
-  float2* res = run_fft(b0, b1, tw, prm.fp, PAIRS, NS);
+  ct_stage<N, R1, R0, R0, THREADS>(b0, b1, tw, PAIRS, BS);
+  __syncthreads();
+  float2* res = b1;
+  if (R2 > 1) {
+    ct_stage<N, (R2 > 1 ? R2 : 2), R0 * R1, R0, THREADS>(b1, b0, tw, PAIRS, BS);
+    __syncthreads();
+    res = b0;
+  }
 
   // ---- split, truncate, scale, store: item = (m, p, kk), kk fastest -> 32-byte sectors
   const int total = prm.mmax * 2 * KC;
-  for (int e = threadIdx.x; e < total; e += kFftThreads) {
+  for (int e = threadIdx.x; e < total; e += THREADS) {
     const int kk = e % KC;
     const int mp = e / KC;
     const int p = mp & 1, m = mp >> 1;
     const int q = kk >> 1;
-    const float2 Z = res[q * NS + m];
-    const float2 Zm = res[q * NS + (m == 0 ? 0 : N - m)];
+    const float2 Z = res[q * BS + skew<R0>(m)];
+    const float2 Zm = res[q * BS + skew<R0>(m == 0 ? 0 : N - m)];
     float2 A, Bq;
     split_pair(Z, Zm, A, Bq);
     const float2 val = (kk & 1) ? Bq : A;
-    float v = p ? val.y : val.x;
     const int k = k0 + kk;
-    float sc;
-    if (prm.scale_mode == 0) sc = prm.rowscale[k];
-    else sc = (m == 0 || 2 * m == N) ? 1.f : 2.f;
-    // rows in the k padding (k >= nlat) are written as exact zeros (pair splitting leaves rounding noise there)
-    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (k < prm.nlat) ? v * sc : 0.f;
+    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (p ? val.y : val.x) * mode_scale_analysis(prm, m, k);
   }
 }
 
-// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]
-template <typename T, int PAIRS>
-__global__ void __launch_bounds__(kFftThreads) fft_synthesis_kernel(const float* __restrict__ Zs, T* __restrict__ y,
-                                                                    const FftParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = prm.nlon;
-  const int NS = N + 1;
-  float2* tw = reinterpret_cast<float2*>(smem_raw);
-  float2* b0 = tw + N;
-  float2* b1 = b0 + PAIRS * NS;
-  constexpr int KC = 2 * PAIRS;
-  const int k0 = blockIdx.x * KC;
-  const int r = blockIdx.y;
-  const int mmax = prm.mmax;
-
-  for (int t = threadIdx.x; t < N; t += kFftThreads) tw[t] = prm.twiddle[t];
-  // zero the untouched middle of the spectrum: indices [mmax, N - mmax]
+// Hermitian-extend the truncated half spectra of rows a = k0+2q, b = a+1 into V = Za + i Zb, stored with real/imag swapped
+// (inverse FFT == swap o forward FFT o swap); `IDX` maps a spectrum index to its (possibly skewed) buffer slot.
+template <class IDX>
+__device__ __forceinline__ void fill_spectrum(const float* __restrict__ Zs, float2* b0, int bufstride, int pairs, int nthreads, const FftParams& prm,
+                                              int k0, int r, IDX idx) {
+  const int N = prm.nlon, mmax = prm.mmax;
   {
-    const int lo = mmax, hi = N - mmax;  // inclusive
-    const int span = hi - lo + 1;
+    const int lo = mmax, span = N - 2 * mmax + 1;  // untouched middle of the spectrum: indices [mmax, N - mmax]
     if (span > 0)
-      for (int e = threadIdx.x; e < PAIRS * span; e += kFftThreads) {
+      for (int e = threadIdx.x; e < pairs * span; e += nthreads) {
         const int q = e / span, i = e - q * span;
-        b0[q * NS + lo + i] = make_float2(0.f, 0.f);
+        b0[q * bufstride + idx(lo + i)] = make_float2(0.f, 0.f);
       }
   }
-  // Hermitian-extend the truncated half spectra of rows a = k0+2q, b = a+1 into V = Za + i Zb and store it with
-  // real/imag swapped (inverse FFT == swap o forward FFT o swap).
-  for (int e = threadIdx.x; e < mmax * PAIRS; e += kFftThreads) {
-    const int q = e % PAIRS, m = e / PAIRS;
+  for (int e = threadIdx.x; e < mmax * pairs; e += nthreads) {
+    const int q = e % pairs, m = e / pairs;
     const int ka = k0 + 2 * q;
     const float2 re2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 0) * prm.R + r) * prm.kp + ka);
     const float2 im2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 1) * prm.R + r) * prm.kp + ka);
@@ -339,70 +375,170 @@ __global__ void __launch_bounds__(kFftThreads) fft_synthesis_kernel(const float*
     if (self_conj) { ai = 0.f; bi = 0.f; }
     if (prm.scale_mode == 1 && !self_conj) { ar *= 0.5f; ai *= 0.5f; br *= 0.5f; bi *= 0.5f; }
     // V[m] = (ar - bi) + i (ai + br);  V[N-m] = (ar + bi) + i (br - ai)   -- stored swapped (y, x)
-    b0[q * NS + m] = make_float2(ai + br, ar - bi);
-    if (!self_conj) b0[q * NS + N - m] = make_float2(br - ai, ar + bi);
+    b0[q * bufstride + idx(m)] = make_float2(ai + br, ar - bi);
+    if (!self_conj) b0[q * bufstride + idx(N - m)] = make_float2(br - ai, ar + bi);
   }
+}
+
+// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]
+template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
+__global__ void __launch_bounds__(THREADS) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
+  constexpr int N = R0 * R1 * R2;
+  constexpr int BS = ct_bufstride<N, R0>();
+  constexpr int KC = 2 * PAIRS;
+  constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
+  constexpr int NsL = N / RL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* b0 = tw + N;
+  float2* b1 = b0 + PAIRS * BS;
+  const int k0 = blockIdx.x * KC;
+  const int r = blockIdx.y;
+  for (int t = threadIdx.x; t < N; t += THREADS) tw[t] = prm.twiddle[t];
+  fill_spectrum(Zs, b0, BS, PAIRS, THREADS, prm, k0, r, [](int i) { return skew<R0>(i); });
   __syncthreads();
-
-  float2* res = run_fft(b0, b1, tw, prm.fp, PAIRS, NS);
-
-  // ---- store rows: a[j] = res.y, b[j] = res.x (swapped back)
+  // stage 0: b0 -> b1
+  ct_stage<N, R0, 1, R0, THREADS>(b0, b1, tw, PAIRS, BS);
+  __syncthreads();
+  const float2* src = b1;
+  if (R2 > 1) {
+    ct_stage<N, R1, R0, R0, THREADS>(b1, b0, tw, PAIRS, BS);
+    __syncthreads();
+    src = b0;
+  }
+  // last stage fused with the store: butterfly j produces natural-order outputs j + rr * NsL;  a[e] = v.y, b[e] = v.x
   {
-    const float* rf = reinterpret_cast<const float*>(res);
     T* base = y + ((size_t)r * prm.nlat + k0) * N;
-    const int rows_valid = min(KC, prm.nlat - k0);
     const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
-    constexpr int V = 16 / sizeof(T);
-    const bool vec_ok = (N % V == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
-    if (vec_ok) {
-      const int nv = N / V;
-      for (int e = threadIdx.x; e < rows_valid * nv; e += kFftThreads) {
-        const int kk = e / nv, jv = e - kk * nv;
-        const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + kk] : 1.f;
-        const float* src = rf + ((size_t)(kk >> 1) * NS + jv * V) * 2 + (1 - (kk & 1));
-        uint4 raw;
-        T* pv = reinterpret_cast<T*>(&raw);
+    for (int w = threadIdx.x; w < PAIRS * NsL; w += THREADS) {
+      const int q = w / NsL, j = w - q * NsL;
+      const float2* s = src + q * BS;
+      float2 v[RL];
 #pragma unroll
-        for (int i = 0; i < V; ++i) st_from_float(pv + i, src[2 * i] * sc + bias);
-        *(reinterpret_cast<uint4*>(base + (size_t)kk * N) + jv) = raw;
+      for (int rr = 0; rr < RL; ++rr) {
+        float2 a = s[skew<R0>(j + rr * NsL)];
+        if (rr > 0) a = cmul(a, tw[rr * j]);   // k = j, N / (Ns * R) = 1
+        v[rr] = a;
       }
-    } else {
-      for (int e = threadIdx.x; e < rows_valid * N; e += kFftThreads) {
-        const int kk = e / N, j = e - kk * N;
-        const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + kk] : 1.f;
-        st_from_float(base + (size_t)kk * N + j, rf[((size_t)(kk >> 1) * NS + j) * 2 + (1 - (kk & 1))] * sc + bias);
+      Butterfly<RL>::run(v, tw, N);
+      const int ka = k0 + 2 * q;
+      const bool va = ka < prm.nlat, vb = ka + 1 < prm.nlat;
+      const float sa = (prm.scale_mode == 1 && va) ? prm.rowscale[ka] : 1.f;
+      const float sb = (prm.scale_mode == 1 && vb) ? prm.rowscale[ka + 1] : 1.f;
+      T* ra = base + (size_t)(2 * q) * N + j;
+      T* rb = ra + N;
+#pragma unroll
+      for (int rr = 0; rr < RL; ++rr) {
+        if (va) st_from_float(ra + rr * NsL, v[rr].y * sa + bias);
+        if (vb) st_from_float(rb + rr * NsL, v[rr].x * sb + bias);
       }
     }
   }
 }
 
-static size_t fft_smem_bytes(int N, int pairs) { return sizeof(float2) * ((size_t)N + 2 * (size_t)pairs * (N + 1)); }
+// ================================================================================================ runtime plans
+constexpr int kFftThreads = 256;
 
-template <typename T, int PAIRS>
-static int launch_analysis(const Plan* pl, const T* x, float* X, FftParams prm, cudaStream_t st) {
-  const size_t smem = fft_smem_bytes(pl->nlon, PAIRS);
-  B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_kernel<T, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(pl->kp / (2 * PAIRS), prm.R);
-  fft_analysis_kernel<T, PAIRS><<<grid, kFftThreads, smem, st>>>(x, X, prm);
-  B200_CHECK_LAUNCH();
-  return 0;
+template <int R>
+__device__ __forceinline__ void run_stage(const float2* in, float2* out, const float2* tw, int N, int Ns, int pairs, int bufstride) {
+  const int nb = N / R;
+  for (int w = threadIdx.x; w < pairs * nb; w += kFftThreads) {
+    const int q = w / nb, j = w - q * nb;
+    stage_butterfly<R>(in + q * bufstride, out + q * bufstride, tw, N, Ns, j);
+  }
+}
+
+// runs all stages; returns pointer to the buffer holding the result
+__device__ __forceinline__ float2* run_fft(float2* b0, float2* b1, const float2* tw, const FftPlan& fp, int pairs, int bufstride) {
+  float2* in = b0;
+  float2* out = b1;
+  int Ns = 1;
+  const int N = fp.N;
+  for (int s = 0; s < fp.nstages; ++s) {
+    const int R = fp.radix[s];
+#define CALL(RR) run_stage<RR>(in, out, tw, N, Ns, pairs, bufstride)
+    B200_RADIX_SWITCH(R, CALL)
+#undef CALL
+    Ns *= R;
+    __syncthreads();
+    float2* t = in; in = out; out = t;
+  }
+  return in;
 }
 
 template <typename T, int PAIRS>
-static int launch_synthesis(const Plan* pl, const float* Z, T* y, FftParams prm, cudaStream_t st) {
-  const size_t smem = fft_smem_bytes(pl->nlon, PAIRS);
-  B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_kernel<T, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(pl->kp / (2 * PAIRS), prm.R);
-  fft_synthesis_kernel<T, PAIRS><<<grid, kFftThreads, smem, st>>>(Z, y, prm);
-  B200_CHECK_LAUNCH();
-  return 0;
+__global__ void __launch_bounds__(kFftThreads) fft_analysis_rt_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = prm.nlon;
+  const int NS = N + 1;  // padded per-pair stride (float2 units)
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* b0 = tw + N;
+  float2* b1 = b0 + PAIRS * NS;
+  constexpr int KC = 2 * PAIRS;
+  const int k0 = blockIdx.x * KC;
+  const int r = blockIdx.y;
+  for (int t = threadIdx.x; t < N; t += kFftThreads) tw[t] = prm.twiddle[t];
+  {
+    float* bf = reinterpret_cast<float*>(b0);
+    const T* base = x + ((size_t)r * prm.nlat + k0) * N;
+    const int rows_valid = min(KC, prm.nlat - k0);
+    for (int e = threadIdx.x; e < KC * N; e += kFftThreads) {
+      const int kk = e / N, j = e - kk * N;
+      const float v = (kk < rows_valid) ? ld_as_float(base + (size_t)kk * N + j) : 0.f;
+      bf[((size_t)(kk >> 1) * NS + j) * 2 + (kk & 1)] = v;
+    }
+  }
+  __syncthreads();
+  float2* res = run_fft(b0, b1, tw, prm.fp, PAIRS, NS);
+  const int total = prm.mmax * 2 * KC;
+  for (int e = threadIdx.x; e < total; e += kFftThreads) {
+    const int kk = e % KC;
+    const int mp = e / KC;
+    const int p = mp & 1, m = mp >> 1;
+    const int q = kk >> 1;
+    float2 A, Bq;
+    split_pair(res[q * NS + m], res[q * NS + (m == 0 ? 0 : N - m)], A, Bq);
+    const float2 val = (kk & 1) ? Bq : A;
+    const int k = k0 + kk;
+    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (p ? val.y : val.x) * mode_scale_analysis(prm, m, k);
+  }
 }
 
-static int pick_pairs(int N) {
-  // shared memory budget: aim for >= 2 CTAs per SM when possible (227 KB per SM)
-  if (fft_smem_bytes(N, 4) <= 110 * 1024) return 4;
-  if (fft_smem_bytes(N, 2) <= 220 * 1024) return 2;
-  if (fft_smem_bytes(N, 1) <= 220 * 1024) return 1;
+template <typename T, int PAIRS>
+__global__ void __launch_bounds__(kFftThreads) fft_synthesis_rt_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = prm.nlon;
+  const int NS = N + 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* b0 = tw + N;
+  float2* b1 = b0 + PAIRS * NS;
+  constexpr int KC = 2 * PAIRS;
+  const int k0 = blockIdx.x * KC;
+  const int r = blockIdx.y;
+  for (int t = threadIdx.x; t < N; t += kFftThreads) tw[t] = prm.twiddle[t];
+  fill_spectrum(Zs, b0, NS, PAIRS, kFftThreads, prm, k0, r, [](int i) { return i; });
+  __syncthreads();
+  float2* res = run_fft(b0, b1, tw, prm.fp, PAIRS, NS);
+  {
+    const float* rf = reinterpret_cast<const float*>(res);
+    T* base = y + ((size_t)r * prm.nlat + k0) * N;
+    const int rows_valid = min(KC, prm.nlat - k0);
+    const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
+    for (int e = threadIdx.x; e < rows_valid * N; e += kFftThreads) {
+      const int kk = e / N, j = e - kk * N;
+      const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + kk] : 1.f;
+      st_from_float(base + (size_t)kk * N + j, rf[((size_t)(kk >> 1) * NS + j) * 2 + (1 - (kk & 1))] * sc + bias);
+    }
+  }
+}
+
+// ===================================================================================================== dispatch
+static size_t rt_smem_bytes(int N, int pairs) { return sizeof(float2) * ((size_t)N + 2 * (size_t)pairs * (N + 1)); }
+
+static int rt_pick_pairs(int N) {
+  if (rt_smem_bytes(N, 4) <= 110 * 1024) return 4;
+  if (rt_smem_bytes(N, 2) <= 220 * 1024) return 2;
+  if (rt_smem_bytes(N, 1) <= 220 * 1024) return 1;
   return 0;
 }
 
@@ -415,43 +551,97 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
   return prm;
 }
 
+template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
+static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
+  constexpr int N = R0 * R1 * R2;
+  constexpr size_t smem = sizeof(float2) * ((size_t)N + 2 * PAIRS * ct_bufstride<N, R0>());
+  static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
+  dim3 grid(pl->kp / (2 * PAIRS), prm.R);
+  if (dir == 0) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2><<<grid, THREADS, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
+  } else {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_synthesis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2><<<grid, THREADS, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
+  }
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// lengths with a compile-time plan: (PAIRS, THREADS, R0, R1, R2); must equal make_fft_plan's choice for N = R0*R1*R2
+#define CT_PLANS(X)        \
+  X(4, 256, 12, 12, 10)    /* 1440 */ \
+  X(4, 256, 10, 9, 8)      /*  720 */ \
+  X(4, 256, 10, 8, 6)      /*  480 */ \
+  X(4, 256, 10, 6, 6)      /*  360 */ \
+  X(4, 128, 15, 12, 1)     /*  180 */ \
+  X(4, 128, 16, 8, 1)      /*  128 */ \
+  X(4, 128, 12, 8, 1)      /*   96 */ \
+  X(4, 64, 9, 8, 1)        /*   72 */ \
+  X(4, 64, 8, 8, 1)        /*   64 */ \
+  X(4, 256, 16, 16, 1)     /*  256 */ \
+  X(4, 256, 8, 8, 8)       /*  512 */ \
+  X(4, 256, 16, 8, 8)      /* 1024 */ \
+  X(2, 256, 16, 15, 12)    /* 2880 */
+
+template <typename T>
+static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st, bool* handled) {
+  const FftPlan& fp = pl->fft;
+  const int r0 = fp.radix[0], r1 = fp.nstages > 1 ? fp.radix[1] : 1, r2 = fp.nstages > 2 ? fp.radix[2] : 1;
+  *handled = true;
+  if (fp.nstages >= 2 && fp.nstages <= 3) {
+#define X(P, TH, A, B_, C_) \
+  if (r0 == A && r1 == B_ && r2 == C_) return launch_ct<T, P, TH, A, B_, C_>(pl, dir, in, out, prm, st);
+    CT_PLANS(X)
+#undef X
+  }
+  *handled = false;
+  return 0;
+}
+
+// pairs per CTA for plan lookup by the grid computation (kp / (2 * pairs) must be integral: kp is a multiple of 8)
+template <typename T>
+static int launch_rt(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
+  const int pairs = rt_pick_pairs(pl->nlon);
+  if (pairs == 0) { set_error("fft: nlon=%d too large for shared memory", pl->nlon); return B200SHT_ERR_UNSUPPORTED; }
+  const size_t smem = rt_smem_bytes(pl->nlon, pairs);
+  dim3 grid(pl->kp / (2 * pairs), prm.R);
+#define LAUNCH(P)                                                                                                                          \
+  if (dir == 0) {                                                                                                                          \
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_rt_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    fft_analysis_rt_kernel<T, P><<<grid, kFftThreads, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);                \
+  } else {                                                                                                                                 \
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_rt_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    fft_synthesis_rt_kernel<T, P><<<grid, kFftThreads, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);               \
+  }
+  if (pairs == 4) { LAUNCH(4) } else if (pairs == 2) { LAUNCH(2) } else { LAUNCH(1) }
+#undef LAUNCH
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+template <typename T>
+static int run_fft_dir(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
+  bool handled = false;
+  int rc = dispatch_ct<T>(pl, dir, in, out, prm, st, &handled);
+  if (handled) return rc;
+  return launch_rt<T>(pl, dir, in, out, prm, st);
+}
+
 int fft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int scale_mode, cudaStream_t st) {
   B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "fft_analysis: B*C=%lld out of range", (long long)B * C);
-  const int pairs = pick_pairs(pl->nlon);
-  if (pairs == 0) { set_error("fft_analysis: nlon=%d too large for shared memory", pl->nlon); return B200SHT_ERR_UNSUPPORTED; }
   FftParams prm = make_params(pl, B, C, scale_mode, nullptr);
-#define DISPATCH(T, P) return launch_analysis<T, P>(pl, static_cast<const T*>(x), X, prm, st)
-  if (dtype == B200SHT_F32) {
-    if (pairs == 4) DISPATCH(float, 4);
-    if (pairs == 2) DISPATCH(float, 2);
-    DISPATCH(float, 1);
-  } else if (dtype == B200SHT_BF16) {
-    if (pairs == 4) DISPATCH(__nv_bfloat16, 4);
-    if (pairs == 2) DISPATCH(__nv_bfloat16, 2);
-    DISPATCH(__nv_bfloat16, 1);
-  }
-#undef DISPATCH
+  if (dtype == B200SHT_F32) return run_fft_dir<float>(pl, 0, x, X, prm, st);
+  if (dtype == B200SHT_BF16) return run_fft_dir<__nv_bfloat16>(pl, 0, x, X, prm, st);
   set_error("fft_analysis: unknown dtype %d", dtype);
   return B200SHT_ERR_INVALID;
 }
 
-int fft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int scale_mode,
-                  cudaStream_t st) {
+int fft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int scale_mode, cudaStream_t st) {
   B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "fft_synthesis: B*C=%lld out of range", (long long)B * C);
-  const int pairs = pick_pairs(pl->nlon);
-  if (pairs == 0) { set_error("fft_synthesis: nlon=%d too large for shared memory", pl->nlon); return B200SHT_ERR_UNSUPPORTED; }
   FftParams prm = make_params(pl, B, C, scale_mode, bias);
-#define DISPATCH(T, P) return launch_synthesis<T, P>(pl, Z, static_cast<T*>(y), prm, st)
-  if (dtype == B200SHT_F32) {
-    if (pairs == 4) DISPATCH(float, 4);
-    if (pairs == 2) DISPATCH(float, 2);
-    DISPATCH(float, 1);
-  } else if (dtype == B200SHT_BF16) {
-    if (pairs == 4) DISPATCH(__nv_bfloat16, 4);
-    if (pairs == 2) DISPATCH(__nv_bfloat16, 2);
-    DISPATCH(__nv_bfloat16, 1);
-  }
-#undef DISPATCH
+  if (dtype == B200SHT_F32) return run_fft_dir<float>(pl, 1, Z, y, prm, st);
+  if (dtype == B200SHT_BF16) return run_fft_dir<__nv_bfloat16>(pl, 1, Z, y, prm, st);
   set_error("fft_synthesis: unknown dtype %d", dtype);
   return B200SHT_ERR_INVALID;
 }
@@ -466,16 +656,9 @@ static void host_fft(std::vector<float2>& a, const std::vector<float2>& tw, cons
   for (int s = 0; s < fp.nstages; ++s) {
     const int R = fp.radix[s];
     for (int j = 0; j < N / R; ++j) {
-      switch (R) {
-        case 2: stage_butterfly<2>(in, out, tw.data(), N, Ns, j); break;
-        case 3: stage_butterfly<3>(in, out, tw.data(), N, Ns, j); break;
-        case 4: stage_butterfly<4>(in, out, tw.data(), N, Ns, j); break;
-        case 5: stage_butterfly<5>(in, out, tw.data(), N, Ns, j); break;
-        case 7: stage_butterfly<7>(in, out, tw.data(), N, Ns, j); break;
-        case 8: stage_butterfly<8>(in, out, tw.data(), N, Ns, j); break;
-        case 11: stage_butterfly<11>(in, out, tw.data(), N, Ns, j); break;
-        default: stage_butterfly<13>(in, out, tw.data(), N, Ns, j); break;
-      }
+#define CALL(RR) stage_butterfly<RR>(in, out, tw.data(), N, Ns, j)
+      B200_RADIX_SWITCH(R, CALL)
+#undef CALL
     }
     Ns *= R;
     float2* t = in; in = out; out = t;
@@ -498,8 +681,7 @@ using namespace b200sht;
 // Debug entry points: run the *same* stage/butterfly/split code on the host (no GPU needed).
 //   analysis : rows a, b (float[N]) -> Xa, Xb (float[2*mmax] interleaved), unscaled rfft
 //   synthesis: Za, Zb (float[2*mmax]) -> rows a, b (float[N]) with irfft(norm="forward") semantics
-extern "C" int b200sht_debug_fft_host(int N, int mmax, int direction, const float* in_a, const float* in_b, float* out_a,
-                                      float* out_b) {
+extern "C" int b200sht_debug_fft_host(int N, int mmax, int direction, const float* in_a, const float* in_b, float* out_a, float* out_b) {
   FftPlan fp;
   if (!make_fft_plan(N, &fp)) { set_error("debug_fft_host: unsupported length %d", N); return B200SHT_ERR_UNSUPPORTED; }
   std::vector<float2> tw;

@@ -112,20 +112,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // ------------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO (all >> 4), version = 1 (bit 46),
 // layout type SWIZZLE_128B = 2 (bits 61..63).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= layout_type << 61;
   return d;
 }
 // K-major operand tile: rows of 128 B (32 floats of K), 8-row groups 1024 B apart.  kstep selects the K = 8 slice (32 B).
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) { return make_smem_desc(tile + kstep * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) { return make_smem_desc(tile + kstep * 32, 16, 1024, 2 /*SWIZZLE_128B*/); }
 // MN-major operand tile: blocks of [32 K-rows][32 floats of M/N]; blocks `blk_bytes` apart; kstep selects 8 K-rows (1024 B).
+// 32-bit MN-major operands use SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom, Swizzle<2,5,2>): atoms of 4 K-rows x 128 B,
+// so one K = 8 MMA spans two atoms SBO = 512 B apart; LBO = distance between 32-float M/N blocks.
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep, uint32_t blk_bytes) {
-  return make_smem_desc(tile + kstep * 1024, blk_bytes, 1024);
+  return make_smem_desc(tile + kstep * 1024, blk_bytes, 512, 1 /*SWIZZLE_128B_BASE32B*/);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::tf32, fp32 accumulate, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_mn_major, int negate_a) {
@@ -502,7 +504,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 // fp32 tensor map, 128-byte swizzle.  dims[0] is the contiguous dimension; strides (in floats) for dims 1..rank-1.
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides, const int* box) {
+// mn_major: the operand is read M/N-major by kind::tf32, which needs the 128-byte swizzle with 32-byte atoms
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides, const int* box, bool mn_major = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
   cuuint64_t gd[5], gs[4];
@@ -514,7 +517,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { set_error("tensor map base is not 16-byte aligned"); return B200SHT_ERR_INVALID; }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return B200SHT_ERR_CUDA; }
   return 0;
 }
@@ -600,13 +604,13 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   {
     long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
     int bx[3] = {32, 32, 1};
-    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx);
+    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx, true);
     if (rc) return rc;
   }
   {
     long long d[3] = {JP, pl->mmax, pl->lmax}, s[3] = {1, JP, (long long)pl->mmax * JP};
     int bx[3] = {32, 1, 32};
-    int rc = make_tmap(&p.tmB, spec, 3, d, s, bx);
+    int rc = make_tmap(&p.tmB, spec, 3, d, s, bx, true);
     if (rc) return rc;
   }
   pick_stages(&p, 16384 + 4096 * p.nblk, ceil_div(pl->lmax, 32));
@@ -617,21 +621,22 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
 }
 
 // --------------------------------------------------------------------------------------------------- mix
-static int spec_tmap(CUtensorMap* tm, const float* base, int L, int M, int B, int Ctot, int cp, int box_c, int box_b, int box_m) {
+static int spec_tmap(CUtensorMap* tm, const float* base, int L, int M, int B, int Ctot, int cp, int box_c, int box_b, int box_m, bool mn_major = false) {
   long long d[5] = {Ctot, B, 2, M, L};
   long long s[5] = {1, cp, (long long)B * cp, 2ll * B * cp, (long long)M * 2 * B * cp};
   int bx[5] = {box_c, box_b, 1, box_m, 1};
-  return make_tmap(tm, base, 5, d, s, bx);
+  return make_tmap(tm, base, 5, d, s, bx, mn_major);
 }
-static int weight_tmap(CUtensorMap* tm, const float* base, int Lw, int G, int Cig, int Cog, int cop, int box_o, int box_i) {
+static int weight_tmap(CUtensorMap* tm, const float* base, int Lw, int G, int Cig, int Cog, int cop, int box_o, int box_i, bool mn_major = false) {
   long long d[4] = {Cog, 2, Cig, (long long)Lw * G};
   long long s[4] = {1, cop, 2ll * cop, (long long)Cig * 2 * cop};
   int bx[4] = {box_o, 1, box_i, 1};
-  return make_tmap(tm, base, 4, d, s, bx);
+  return make_tmap(tm, base, 4, d, s, bx, mn_major);
 }
 
 static int fill_mix(const Plan* pl, int op, int B, int G, int Ci, int Co, MixParams* p) {
   B200_REQUIRE(B >= 1 && 32 % B == 0, "tcgen05 mix: batch %d must divide 32 (use precision fp32 otherwise)", B);
+  B200_REQUIRE(G == 1 || ((Ci / G) % 4 == 0 && (Co / G) % 4 == 0), "tcgen05 mix: group slices (%d, %d channels) must be 16-byte aligned", Ci / G, Co / G);
   memset(p, 0, sizeof(*p));
   p->L = pl->lmax; p->M = pl->mmax; p->B = B; p->G = G; p->Cig = Ci / G; p->Cog = Co / G;
   p->cpi = round_up(Ci, 4); p->cpo = round_up(Co, 4); p->cop = round_up(Co / G, 4);
@@ -654,7 +659,7 @@ int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, cons
   p.idesc_neg = make_idesc(p.N, 0, 1, 1);
   p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;
   rc = spec_tmap(&p.tmX, x, p.L, p.M, B, Ci, p.cpi, 32, B, p.Mt);
-  if (!rc) rc = weight_tmap(&p.tmW, static_cast<const float*>(w), p.shared_w ? 1 : p.L, G, p.Cig, p.Cog, p.cop, 32, 32);
+  if (!rc) rc = weight_tmap(&p.tmW, static_cast<const float*>(w), p.shared_w ? 1 : p.L, G, p.Cig, p.Cog, p.cop, 32, 32, true);
   if (rc) return rc;
   pick_stages(&p, 32768 + 8192 * p.nblk, ceil_div(p.Cig, 32));
   p.tx_bytes = 2u * (uint32_t)(p.Mt * B) * 128 + 8192u * p.nblk;
@@ -699,8 +704,8 @@ int mix_wgrad_umma(const Plan* pl, int op, const float* x, const float* gy, floa
   p.idesc = make_idesc(p.N, 1, 1, 0);
   p.idesc_neg = make_idesc(p.N, 1, 1, 1);
   p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;
-  rc = spec_tmap(&p.tmX, x, p.L, p.M, B, Ci, p.cpi, 32, B, 32 / B);
-  if (!rc) rc = spec_tmap(&p.tmX2, gy, p.L, p.M, B, Co, p.cpo, 32, B, 32 / B);
+  rc = spec_tmap(&p.tmX, x, p.L, p.M, B, Ci, p.cpi, 32, B, 32 / B, true);
+  if (!rc) rc = spec_tmap(&p.tmX2, gy, p.L, p.M, B, Co, p.cpo, 32, B, 32 / B, true);
   if (rc) return rc;
   pick_stages(&p, 32768 + 8192 * p.nblk, 8);
   p.tx_bytes = 32768u + 8192u * p.nblk;

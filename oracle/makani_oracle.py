@@ -223,9 +223,10 @@ def complex_relu(z, mode="real", bias=0.0, negative_slope=0.0):
         cond = torch.logical_and(ang >= 0.0, ang < math.pi / 2.0)
         return torch.where(cond, z, negative_slope * z)
     if mode == "real":
-        zr = torch.view_as_real(z).clone()
-        zr[..., 0] = act(zr[..., 0])
-        return torch.view_as_complex(zr)
+        zr = torch.view_as_real(z)
+        outr = zr.clone()
+        outr[..., 0] = act(zr[..., 0])
+        return torch.view_as_complex(outr)
     raise NotImplementedError(mode)
 
 

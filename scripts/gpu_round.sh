@@ -9,6 +9,7 @@ timeout 1500 python -m pytest tests/test_gpu_umma.py -m gpu -q -rA --timeout=900
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --steps 50 --warmup 5 --precision fp32 --no-cpu > gpurun_out/bench_fp32.json 2>> gpurun_out/bench.err
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload sfno_block_240x480x384 > gpurun_out/bench_2a.json 2>> gpurun_out/bench.err
 echo "=== diag"; grep -E "^---|rel_l2|failures|!" gpurun_out/umma_diag.log | cut -c1-260 | tail -120
 echo "=== pytest"; tail -40 gpurun_out/pytest_gpu.log | cut -c1-200; echo "=== pytest umma"; tail -40 gpurun_out/pytest_umma.log | cut -c1-200
 echo "=== smoke"; tail -3 gpurun_out/smoke.log; echo "=== bench"; cat gpurun_out/bench.json | cut -c1-2500; tail -5 gpurun_out/bench.err

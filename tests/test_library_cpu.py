@@ -48,7 +48,8 @@ def test_fft_plan_factorisation(N):
     rad = np.zeros(20, dtype=np.int32)
     n = lib.b200sht_debug_fft_plan(N, _p(rad), 20)
     assert n > 0 and int(np.prod(rad[:n])) == N
-    assert set(rad[:n]) <= {2, 3, 4, 5, 7, 8, 11, 13}
+    assert set(rad[:n].tolist()) <= {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16}
+    assert list(rad[:n]) == sorted(rad[:n], reverse=True)
 
 
 def test_fft_plan_rejects_large_primes():
