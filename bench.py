@@ -333,7 +333,7 @@ def run_gpu_arm(args):
         sp_a = torch.zeros(plan_f.spec_elems(B, C), device=dev)
         sp_b = torch.zeros(plan_f.spec_elems(B, C), device=dev)
         sp_c = torch.zeros(plan_f.spec_elems(B, C), device=dev)
-        wpk = conv._wcache.get(conv.weight, _lib.OP_DHCONV, L, M, 1, C, C)
+        wpk = conv._wcache.get(conv.weight, _lib.OP_DHCONV, L, M, 1, C, C, prec)
         gwpk = torch.empty_like(wpk)
         y_dev = torch.empty(1, C, nlat_o, nlon_o, device=dev, dtype=act_dtype)
         gx_dev = torch.empty_like(x_dev)

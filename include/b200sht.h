@@ -92,7 +92,8 @@ int64_t b200sht_spec_elems_lm(int L, int M, int B, int C);
 /* Longitude analysis: real rows -> truncated half spectrum.
  *   X[m][p][r][k] = row_scale[k] * mode_scale[m] * sum_j x[r][k][j] exp(-2 pi i m j / nlon)
  * scale_mode 0: SHT forward     (row_scale = quad_w[k] * 2 pi / nlon, mode_scale = 1)
- * scale_mode 1: adjoint of irfft (row_scale = 1, mode_scale = 1 for m = 0 and Nyquist, 2 otherwise) */
+ * scale_mode 1: adjoint of irfft (row_scale = 1, mode_scale = 1 for m = 0 and Nyquist, 2 otherwise)
+ * scale_mode | 2: additionally round the output to the nearest TF32 value (it is the operand of a kind::tf32 GEMM) */
 int b200sht_fft_analysis(const b200sht_plan* plan, const void* x, int dtype, int B, int C,
                          float* latspec, int scale_mode, void* stream);
 /* Longitude synthesis: truncated half spectrum -> real rows (+ optional per-channel bias, cast to dtype).
@@ -132,7 +133,7 @@ int b200sht_sht_inverse_adjoint(const b200sht_plan* plan, const void* gy, int dt
  * float [L][G][Ci/G][2][cop] (real and imaginary planes; cop = Co/G rounded up to 4; l-stride 0 for OP_SHARED).  Only the dense
  * operators (DHCONV, SHARED, LDEP) use a packed weight; the others read the native layout. */
 int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co);
-int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, void* stream);
+int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int precision, void* stream);
 int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int L, int G, int Ci, int Co, void* stream);
 
 /* y[l][m][.][b][o] = sum_i x[l][m][.][b][i] * w[...]   on packed spec tensors (x: C = Ci, y: C = Co).

@@ -29,7 +29,7 @@ int legendre_synthesis_simt(const Plan* pl, const float* spec, float* Z, int B, 
 int spec_unpack(const Plan* pl, const float* spec, void* coeffs, int B, int C, cudaStream_t st);
 int spec_pack(const Plan* pl, const void* coeffs, float* spec, int B, int C, cudaStream_t st);
 int bias_grad(const Plan* pl, const float* X, float* gbias, int B, int C, cudaStream_t st);
-int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, cudaStream_t st);
+int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, int round_tf32, cudaStream_t st);
 int mix_forward_simt(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
 int mix_backward_simt(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
                       int Ci, int Co, cudaStream_t st);
@@ -156,7 +156,7 @@ int64_t b200sht_spec_elems_lm(int L, int M, int B, int C) { return (int64_t)L * 
 // -------------------------------------------------------------------------------------------- stages
 int b200sht_fft_analysis(const b200sht_plan* pl, const void* x, int dtype, int B, int C, float* latspec, int scale_mode, void* stream) {
   B200_REQUIRE(pl && x && latspec, "fft_analysis: null argument");
-  B200_REQUIRE(scale_mode == 0 || scale_mode == 1, "fft_analysis: bad scale_mode %d", scale_mode);
+  B200_REQUIRE(scale_mode >= 0 && scale_mode <= 3, "fft_analysis: bad scale_mode %d", scale_mode);
   return fft_analysis(pl, x, dtype, B, C, latspec, scale_mode, S(stream));
 }
 
@@ -228,7 +228,7 @@ int b200sht_sht_forward(const b200sht_plan* pl, const void* x, int dtype, int B,
   B200_REQUIRE(pl && x && coeffs && ws, "sht_forward: null argument");
   float *X, *sp;
   split_ws(pl, B, C, ws, &X, &sp);
-  int rc = b200sht_fft_analysis(pl, x, dtype, B, C, X, 0, stream);
+  int rc = b200sht_fft_analysis(pl, x, dtype, B, C, X, 0 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
   if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, coeffs, B, C, stream);
   return rc;
@@ -260,7 +260,7 @@ int b200sht_sht_inverse_adjoint(const b200sht_plan* pl, const void* gy, int dtyp
   B200_REQUIRE(pl && gy && gcoeffs && ws, "sht_inverse_adjoint: null argument");
   float *X, *sp;
   split_ws(pl, B, C, ws, &X, &sp);
-  int rc = b200sht_fft_analysis(pl, gy, dtype, B, C, X, 1, stream);
+  int rc = b200sht_fft_analysis(pl, gy, dtype, B, C, X, 1 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
   if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, gcoeffs, B, C, stream);
   return rc;
@@ -281,13 +281,13 @@ int64_t b200sht_mix_weight_elems(int op, int L, int M, int G, int Ci, int Co) {
   }
 }
 
-int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, void* stream) {
+int b200sht_mix_weight_pack(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int precision, void* stream) {
   B200_REQUIRE(w_native && w_packed, "mix_weight_pack: null argument");
-  return mix_weight_relayout(op, w_native, w_packed, L, G, Ci, Co, 0, S(stream));
+  return mix_weight_relayout(op, w_native, w_packed, L, G, Ci, Co, 0, precision == B200SHT_PREC_TF32, S(stream));
 }
 int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int L, int G, int Ci, int Co, void* stream) {
   B200_REQUIRE(w_native && w_packed, "mix_weight_unpack: null argument");
-  return mix_weight_relayout(op, w_native, const_cast<float*>(w_packed), L, G, Ci, Co, 1, S(stream));
+  return mix_weight_relayout(op, w_native, const_cast<float*>(w_packed), L, G, Ci, Co, 1, 0, S(stream));
 }
 
 static bool dense_op(int op) { return op == B200SHT_OP_DHCONV || op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP; }
@@ -373,7 +373,7 @@ int b200sht_spectral_conv_forward(const b200sht_plan* f, const b200sht_plan* v, 
   B200_REQUIRE(x && w && y && workspace, "spectral_conv_forward: null argument");
   ConvWs ws = conv_ws(f, v, d, workspace);
   float* spec_x = spec_x_saved ? spec_x_saved : ws.spec_in;
-  rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0, stream);
+  rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc) rc = b200sht_legendre_analysis(f, ws.lat_in, spec_x, d->B, d->Cin, d->precision, stream);
   if (!rc && residual) {
     rc = b200sht_legendre_synthesis(v, spec_x, ws.lat_out, d->B, d->Cin, d->precision, stream);
@@ -399,14 +399,14 @@ int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v,
   B200_REQUIRE(gw == nullptr || spec_x_saved != nullptr, "spectral_conv_backward: weight gradient needs the saved spectrum");
   ConvWs ws = conv_ws(f, v, d, workspace);
   // dL/d(spec_out) = analysis_v(fft_v(gy, adjoint scaling))
-  rc = b200sht_fft_analysis(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, 1, stream);
+  rc = b200sht_fft_analysis(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc && gbias) rc = b200sht_bias_grad(v, ws.lat_out, gbias, d->B, d->Cout, stream);
   if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cout, d->precision, stream);
   if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, gx ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G, d->Cin, d->Cout,
                                      d->precision, stream);
   if (!rc && gx) {
     if (gresidual) {
-      rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1, stream);
+      rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
       if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cin, d->precision, stream);
       if (!rc) {
         const long long n = b200sht_spec_elems(f, d->B, d->Cin);

@@ -32,6 +32,14 @@ void set_error(const char* fmt, ...);
     }                                           \
   } while (0)
 
+// round-to-nearest conversion to TF32 (10-bit mantissa), as cuBLAS applies to its TF32 GEMM inputs; tcgen05 kind::tf32 itself
+// truncates the low 13 mantissa bits of whatever it reads, so producers of tensor-core operands round first.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 HD int round_up(int a, int b) { return (a + b - 1) / b * b; }
 HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -52,6 +60,7 @@ struct Plan {
   int nlat, nlon, lmax, mmax, kp;
   int csphase;
   float* d_table;       // [mmax][lmax][kp]
+  float* d_table_tf32;  // same, rounded to nearest TF32 (operand of the tcgen05 kernels); null when that path is unavailable
   float* d_rowscale;    // [kp]  quad_w[k] * 2 pi / nlon (0 in the padding)
   float2* d_twiddle;    // [nlon] exp(-2 pi i t / nlon)
   FftPlan fft;

@@ -243,6 +243,7 @@ struct FftParams {
   int R;            // B*C image rows
   int C;            // channels (bias index = r % C)
   int scale_mode;
+  int round_tf32;   // analysis output feeds a tcgen05 kind::tf32 GEMM: round to nearest TF32 here
   const float2* twiddle;
   const float* rowscale;
   const float* bias;
@@ -252,6 +253,8 @@ __device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); 
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float finish_analysis(const FftParams& prm, float v) { return prm.round_tf32 ? tf32_rn(v) : v; }
 
 __device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m, int k) {
   if (k >= prm.nlat) return 0.f;  // rows in the k padding are written as exact zeros
@@ -263,27 +266,38 @@ __device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m
 template <int R0>
 __host__ __device__ constexpr int skew(int i) { return i + i / R0; }
 
-// stage s of a compile-time plan: smem (skewed) -> smem (skewed)
-template <int N, int R, int Ns, int R0, int THREADS>
-__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int pairs, int bufstride) {
+// stage s of a compile-time plan: smem (skewed) -> smem (skewed).  One thread owns butterfly index j of ALL pairs: the
+// R-1 twiddles and the 2R skewed indices are computed once and reused for the PAIRS independent transforms.
+template <int N, int R, int Ns, int R0, int THREADS, int PAIRS>
+__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int bufstride) {
   constexpr int NB = N / R;
-  for (int w = threadIdx.x; w < pairs * NB; w += THREADS) {
-    const int q = w / NB, j = w - q * NB;
+  for (int j = threadIdx.x; j < NB; j += THREADS) {
     const int k = j % Ns;
     const int tstep = k * (N / (Ns * R));
-    const float2* src = in + q * bufstride;
-    float2* dst = out + q * bufstride;
-    float2 v[R];
+    const int j0 = (j - k) * R + k;
+    float2 w[R];
+    int si[R], di[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float2 a = src[skew<R0>(j + r * NB)];
-      if (Ns > 1 && r > 0) a = cmul(a, tw[r * tstep]);
-      v[r] = a;
+      si[r] = skew<R0>(j + r * NB);
+      di[r] = skew<R0>(j0 + r * Ns);
+      if (Ns > 1 && r > 0) w[r] = tw[r * tstep];
     }
-    Butterfly<R>::run(v, tw, N);
-    const int j0 = (j - k) * R + k;
+#pragma unroll 2
+    for (int q = 0; q < PAIRS; ++q) {
+      const float2* src = in + q * bufstride;
+      float2* dst = out + q * bufstride;
+      float2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[skew<R0>(j0 + r * Ns)] = v[r];
+      for (int r = 0; r < R; ++r) {
+        float2 a = src[si[r]];
+        if (Ns > 1 && r > 0) a = cmul(a, w[r]);
+        v[r] = a;
+      }
+      Butterfly<R>::run(v, tw, N);
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[di[r]] = v[r];
+    }
   }
 }
 
@@ -308,26 +322,31 @@ __global__ void __launch_bounds__(THREADS) fft_analysis_ct_kernel(const T* __res
   {
     constexpr int NB = N / R0;
     const T* base = x + ((size_t)r * prm.nlat + k0) * N;
-    for (int w = threadIdx.x; w < PAIRS * NB; w += THREADS) {
-      const int q = w / NB, j = w - q * NB;
-      const bool va = (k0 + 2 * q) < prm.nlat, vb = (k0 + 2 * q + 1) < prm.nlat;
-      const T* ra = base + (size_t)(2 * q) * N + j;
-      const T* rb = ra + N;
-      float2 v[R0];
+    for (int j = threadIdx.x; j < NB; j += THREADS) {
+      int di[R0];
 #pragma unroll
-      for (int rr = 0; rr < R0; ++rr) v[rr] = make_float2(va ? ld_as_float(ra + rr * NB) : 0.f, vb ? ld_as_float(rb + rr * NB) : 0.f);
-      Butterfly<R0>::run(v, nullptr, N);
-      float2* dst = b0 + q * BS;
+      for (int rr = 0; rr < R0; ++rr) di[rr] = skew<R0>(j * R0 + rr);
+#pragma unroll 2
+      for (int q = 0; q < PAIRS; ++q) {
+        const bool va = (k0 + 2 * q) < prm.nlat, vb = (k0 + 2 * q + 1) < prm.nlat;
+        const T* ra = base + (size_t)(2 * q) * N + j;
+        const T* rb = ra + N;
+        float2 v[R0];
 #pragma unroll
-      for (int rr = 0; rr < R0; ++rr) dst[skew<R0>(j * R0 + rr)] = v[rr];
+        for (int rr = 0; rr < R0; ++rr) v[rr] = make_float2(va ? ld_as_float(ra + rr * NB) : 0.f, vb ? ld_as_float(rb + rr * NB) : 0.f);
+        Butterfly<R0>::run(v, nullptr, N);
+        float2* dst = b0 + q * BS;
+#pragma unroll
+        for (int rr = 0; rr < R0; ++rr) dst[di[rr]] = v[rr];
+      }
     }
   }
   __syncthreads();
-  ct_stage<N, R1, R0, R0, THREADS>(b0, b1, tw, PAIRS, BS);
+  ct_stage<N, R1, R0, R0, THREADS, PAIRS>(b0, b1, tw, BS);
   __syncthreads();
   float2* res = b1;
   if (R2 > 1) {
-    ct_stage<N, (R2 > 1 ? R2 : 2), R0 * R1, R0, THREADS>(b1, b0, tw, PAIRS, BS);
+    ct_stage<N, (R2 > 1 ? R2 : 2), R0 * R1, R0, THREADS, PAIRS>(b1, b0, tw, BS);
     __syncthreads();
     res = b0;
   }
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(THREADS) fft_analysis_ct_kernel(const T* __res
     split_pair(Z, Zm, A, Bq);
     const float2 val = (kk & 1) ? Bq : A;
     const int k = k0 + kk;
-    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (p ? val.y : val.x) * mode_scale_analysis(prm, m, k);
+    if (k < prm.kp) X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = finish_analysis(prm, (p ? val.y : val.x) * mode_scale_analysis(prm, m, k));
   }
 }
 
@@ -366,8 +385,11 @@ __device__ __forceinline__ void fill_spectrum(const float* __restrict__ Zs, floa
   for (int e = threadIdx.x; e < mmax * pairs; e += nthreads) {
     const int q = e % pairs, m = e / pairs;
     const int ka = k0 + 2 * q;
-    const float2 re2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 0) * prm.R + r) * prm.kp + ka);
-    const float2 im2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 1) * prm.R + r) * prm.kp + ka);
+    float2 re2 = make_float2(0.f, 0.f), im2 = re2;
+    if (ka < prm.kp) {  // kp is a multiple of 8 and ka is even: ka + 1 < kp as well
+      re2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 0) * prm.R + r) * prm.kp + ka);
+      im2 = *reinterpret_cast<const float2*>(Zs + (((size_t)m * 2 + 1) * prm.R + r) * prm.kp + ka);
+    }
     float ar = re2.x, br = re2.y, ai = im2.x, bi = im2.y;
     if (ka >= prm.nlat) { ar = 0.f; ai = 0.f; }
     if (ka + 1 >= prm.nlat) { br = 0.f; bi = 0.f; }
@@ -398,11 +420,11 @@ __global__ void __launch_bounds__(THREADS) fft_synthesis_ct_kernel(const float* 
   fill_spectrum(Zs, b0, BS, PAIRS, THREADS, prm, k0, r, [](int i) { return skew<R0>(i); });
   __syncthreads();
   // stage 0: b0 -> b1
-  ct_stage<N, R0, 1, R0, THREADS>(b0, b1, tw, PAIRS, BS);
+  ct_stage<N, R0, 1, R0, THREADS, PAIRS>(b0, b1, tw, BS);
   __syncthreads();
   const float2* src = b1;
   if (R2 > 1) {
-    ct_stage<N, R1, R0, R0, THREADS>(b1, b0, tw, PAIRS, BS);
+    ct_stage<N, R1, R0, R0, THREADS, PAIRS>(b1, b0, tw, BS);
     __syncthreads();
     src = b0;
   }
@@ -410,27 +432,36 @@ __global__ void __launch_bounds__(THREADS) fft_synthesis_ct_kernel(const float* 
   {
     T* base = y + ((size_t)r * prm.nlat + k0) * N;
     const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
-    for (int w = threadIdx.x; w < PAIRS * NsL; w += THREADS) {
-      const int q = w / NsL, j = w - q * NsL;
-      const float2* s = src + q * BS;
-      float2 v[RL];
+    for (int j = threadIdx.x; j < NsL; j += THREADS) {
+      float2 w[RL];
+      int si[RL];
 #pragma unroll
       for (int rr = 0; rr < RL; ++rr) {
-        float2 a = s[skew<R0>(j + rr * NsL)];
-        if (rr > 0) a = cmul(a, tw[rr * j]);   // k = j, N / (Ns * R) = 1
-        v[rr] = a;
+        si[rr] = skew<R0>(j + rr * NsL);
+        if (rr > 0) w[rr] = tw[rr * j];   // k = j, N / (Ns * R) = 1
       }
-      Butterfly<RL>::run(v, tw, N);
-      const int ka = k0 + 2 * q;
-      const bool va = ka < prm.nlat, vb = ka + 1 < prm.nlat;
-      const float sa = (prm.scale_mode == 1 && va) ? prm.rowscale[ka] : 1.f;
-      const float sb = (prm.scale_mode == 1 && vb) ? prm.rowscale[ka + 1] : 1.f;
-      T* ra = base + (size_t)(2 * q) * N + j;
-      T* rb = ra + N;
+#pragma unroll 2
+      for (int q = 0; q < PAIRS; ++q) {
+        const float2* s = src + q * BS;
+        float2 v[RL];
 #pragma unroll
-      for (int rr = 0; rr < RL; ++rr) {
-        if (va) st_from_float(ra + rr * NsL, v[rr].y * sa + bias);
-        if (vb) st_from_float(rb + rr * NsL, v[rr].x * sb + bias);
+        for (int rr = 0; rr < RL; ++rr) {
+          float2 a = s[si[rr]];
+          if (rr > 0) a = cmul(a, w[rr]);
+          v[rr] = a;
+        }
+        Butterfly<RL>::run(v, tw, N);
+        const int ka = k0 + 2 * q;
+        const bool va = ka < prm.nlat, vb = ka + 1 < prm.nlat;
+        const float sa = (prm.scale_mode == 1 && va) ? prm.rowscale[ka] : 1.f;
+        const float sb = (prm.scale_mode == 1 && vb) ? prm.rowscale[ka + 1] : 1.f;
+        T* ra = base + (size_t)(2 * q) * N + j;
+        T* rb = ra + N;
+#pragma unroll
+        for (int rr = 0; rr < RL; ++rr) {
+          if (va) st_from_float(ra + rr * NsL, v[rr].y * sa + bias);
+          if (vb) st_from_float(rb + rr * NsL, v[rr].x * sb + bias);
+        }
       }
     }
   }
@@ -500,7 +531,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_analysis_rt_kernel(const T* _
     split_pair(res[q * NS + m], res[q * NS + (m == 0 ? 0 : N - m)], A, Bq);
     const float2 val = (kk & 1) ? Bq : A;
     const int k = k0 + kk;
-    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = (p ? val.y : val.x) * mode_scale_analysis(prm, m, k);
+    X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = finish_analysis(prm, (p ? val.y : val.x) * mode_scale_analysis(prm, m, k));
   }
 }
 
@@ -546,7 +577,7 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
   FftParams prm;
   prm.fp = pl->fft;
   prm.nlat = pl->nlat; prm.nlon = pl->nlon; prm.mmax = pl->mmax; prm.kp = pl->kp;
-  prm.R = B * C; prm.C = C; prm.scale_mode = scale_mode;
+  prm.R = B * C; prm.C = C; prm.scale_mode = scale_mode & 1; prm.round_tf32 = (scale_mode >> 1) & 1;
   prm.twiddle = pl->d_twiddle; prm.rowscale = pl->d_rowscale; prm.bias = bias;
   return prm;
 }
@@ -556,7 +587,7 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   constexpr int N = R0 * R1 * R2;
   constexpr size_t smem = sizeof(float2) * ((size_t)N + 2 * PAIRS * ct_bufstride<N, R0>());
   static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
-  dim3 grid(pl->kp / (2 * PAIRS), prm.R);
+  dim3 grid(ceil_div(pl->kp, 2 * PAIRS), prm.R);
   if (dir == 0) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2><<<grid, THREADS, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
@@ -568,33 +599,32 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   return 0;
 }
 
-// lengths with a compile-time plan: (PAIRS, THREADS, R0, R1, R2); must equal make_fft_plan's choice for N = R0*R1*R2
+// lengths with a compile-time plan: (PAIRS, THREADS, R0, R1, R2), N = R0*R1*R2.  R0 is a power of two where possible (the
+// skew i + i/R0 becomes a shift); THREADS ~ max_s N/R_s because one thread owns a butterfly index of all PAIRS transforms.
 #define CT_PLANS(X)        \
-  X(4, 256, 12, 12, 10)    /* 1440 */ \
-  X(4, 256, 10, 9, 8)      /*  720 */ \
-  X(4, 256, 10, 8, 6)      /*  480 */ \
-  X(4, 256, 10, 6, 6)      /*  360 */ \
-  X(4, 128, 15, 12, 1)     /*  180 */ \
-  X(4, 128, 16, 8, 1)      /*  128 */ \
-  X(4, 128, 12, 8, 1)      /*   96 */ \
-  X(4, 64, 9, 8, 1)        /*   72 */ \
-  X(4, 64, 8, 8, 1)        /*   64 */ \
-  X(4, 256, 16, 16, 1)     /*  256 */ \
-  X(4, 256, 8, 8, 8)       /*  512 */ \
-  X(4, 256, 16, 8, 8)      /* 1024 */ \
+  X(4, 160, 16, 10, 9)     /* 1440 */ \
+  X(4, 96, 8, 10, 9)       /*  720 */ \
+  X(4, 96, 8, 10, 6)       /*  480 */ \
+  X(4, 96, 8, 9, 5)        /*  360 */ \
+  X(4, 64, 8, 6, 5)        /*  240 */ \
+  X(4, 64, 4, 9, 5)        /*  180 */ \
+  X(4, 64, 8, 6, 3)        /*  144 */ \
+  X(8, 32, 8, 4, 4)        /*  128 */ \
+  X(8, 32, 8, 4, 3)        /*   96 */ \
+  X(8, 32, 8, 3, 3)        /*   72 */ \
+  X(8, 32, 4, 4, 4)        /*   64 */ \
+  X(8, 64, 16, 4, 4)       /*  256 */ \
+  X(4, 64, 8, 8, 8)        /*  512 */ \
+  X(4, 128, 16, 8, 8)      /* 1024 */ \
   X(2, 256, 16, 15, 12)    /* 2880 */
 
 template <typename T>
 static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st, bool* handled) {
-  const FftPlan& fp = pl->fft;
-  const int r0 = fp.radix[0], r1 = fp.nstages > 1 ? fp.radix[1] : 1, r2 = fp.nstages > 2 ? fp.radix[2] : 1;
   *handled = true;
-  if (fp.nstages >= 2 && fp.nstages <= 3) {
 #define X(P, TH, A, B_, C_) \
-  if (r0 == A && r1 == B_ && r2 == C_) return launch_ct<T, P, TH, A, B_, C_>(pl, dir, in, out, prm, st);
-    CT_PLANS(X)
+  if (pl->nlon == (A) * (B_) * (C_)) return launch_ct<T, P, TH, A, B_, C_>(pl, dir, in, out, prm, st);
+  CT_PLANS(X)
 #undef X
-  }
   *handled = false;
   return 0;
 }

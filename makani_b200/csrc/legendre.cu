@@ -38,6 +38,17 @@ HD void legendre_column(int m, int lmax, double x, int csphase, float* out, size
   }
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = tf32_rn(src[i]);
+}
+
+int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st) {
+  round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 __global__ void build_table_kernel(float* __restrict__ table, const double* __restrict__ cost, int nlat, int kp, int lmax,
                                    int mmax, int csphase) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

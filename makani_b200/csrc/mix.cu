@@ -20,7 +20,7 @@ struct MixDims {
 // ------------------------------------------------------------------------------------ weight re-layout
 // native DHCONV complex [G][Cig][Cog][L]  <->  packed float [L][G][Cig][2][cop]  (real plane, imaginary plane per input row)
 __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restrict__ wn, float* __restrict__ wp, int L, int GC /*G*Cig*/, int Cog,
-                                                                 int cop, int to_native) {
+                                                                 int cop, int to_native, int rnd) {
   __shared__ float2 tile[32][33];
   const int gi = blockIdx.z;
   const int o0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restr
       const int l = l0 + ll, o = o0 + tx;
       if (l < L && o < cop) {
         float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
-        row[o] = tile[tx][ll].x;
-        row[cop + o] = tile[tx][ll].y;
+        row[o] = rnd ? tf32_rn(tile[tx][ll].x) : tile[tx][ll].x;
+        row[cop + o] = rnd ? tf32_rn(tile[tx][ll].y) : tile[tx][ll].y;
       }
     }
   } else {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restr
 }
 
 // native [rows][Co] complex <-> packed [rows][2][cop]   (OP_SHARED: rows = Ci, OP_LDEP: rows = L*Ci)
-__global__ void weight_pad_kernel(float2* __restrict__ wn, float* __restrict__ wp, long long rows, int Co, int cop, int to_native) {
+__global__ void weight_pad_kernel(float2* __restrict__ wn, float* __restrict__ wp, long long rows, int Co, int cop, int to_native, int rnd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cop) return;
   const long long row = idx / cop;
@@ -68,25 +68,25 @@ __global__ void weight_pad_kernel(float2* __restrict__ wn, float* __restrict__ w
   float* prow = wp + row * 2 * cop;
   if (!to_native) {
     const float2 v = (o < Co) ? wn[row * Co + o] : make_float2(0.f, 0.f);
-    prow[o] = v.x;
-    prow[cop + o] = v.y;
+    prow[o] = rnd ? tf32_rn(v.x) : v.x;
+    prow[cop + o] = rnd ? tf32_rn(v.y) : v.y;
   } else if (o < Co) {
     wn[row * Co + o] = make_float2(prow[o], prow[cop + o]);
   }
 }
 
-int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, cudaStream_t st) {
+int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, int G, int Ci, int Co, int to_native, int round_tf32, cudaStream_t st) {
   B200_REQUIRE(G > 0 && Ci % G == 0 && Co % G == 0, "mix_weight: channels (%d,%d) not divisible by groups %d", Ci, Co, G);
   const int Cig = Ci / G, Cog = Co / G, cop = round_up(Cog, 4);
   if (op == B200SHT_OP_DHCONV) {
     dim3 grid(ceil_div(L, 32), ceil_div(cop, 32), G * Cig);
     B200_REQUIRE(grid.z <= 65535, "mix_weight: G*Cig=%u exceeds grid limit", grid.z);
-    weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop, to_native);
+    weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop, to_native, round_tf32);
   } else if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) {
     B200_REQUIRE(G == 1, "mix_weight: OP_SHARED/OP_LDEP are ungrouped");
     const long long rows = (op == B200SHT_OP_SHARED) ? Ci : (long long)L * Ci;
     const long long total = rows * cop;
-    weight_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, rows, Co, cop, to_native);
+    weight_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, rows, Co, cop, to_native, round_tf32);
   } else {
     set_error("mix_weight: operator %d has no packed weight", op);
     return B200SHT_ERR_INVALID;

@@ -247,7 +247,8 @@ struct AnaTraits {
         if (n >= ncols) break;
         const int pbi = n / p.Cc, ci = n - pbi * p.Cc;
         const int pb = t.pb0 + pbi, c = t.c0 + ci;
-        if (pb < p.PB && c < p.cp) *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        if (pb < p.PB && c < p.cp)  // consumers are kind::tf32 MMAs: round to nearest here
+          *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(tf32_rn(v[q * 4]), tf32_rn(v[q * 4 + 1]), tf32_rn(v[q * 4 + 2]), tf32_rn(v[q * 4 + 3]));
       }
     }
   }
@@ -378,8 +379,8 @@ struct MixFwdTraits {
         float a = vr[q], c = vi[q];
         if (o >= NOg) { a = 0.f; c = 0.f; }
         else if (with_bias) { const float2 cb = p.cbias[g * NOg + o]; a += cb.x; c += cb.y; }
-        yr[o] = a;
-        yi[o] = c;
+        yr[o] = tf32_rn(a);
+        yi[o] = tf32_rn(c);
       }
     }
   }
@@ -532,11 +533,25 @@ int umma_available() {
   return g_umma_ok;
 }
 
+int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st);  // legendre.cu
+
 int umma_plan_init(Plan* pl) {
   pl->umma_state = nullptr;
-  return umma_available() ? 0 : -1;
+  pl->d_table_tf32 = nullptr;
+  if (!umma_available()) return -1;
+  const size_t n = (size_t)pl->mmax * pl->lmax * pl->kp;
+  if (cudaMalloc(&pl->d_table_tf32, n * sizeof(float)) != cudaSuccess) { pl->d_table_tf32 = nullptr; return -1; }
+  if (round_table_tf32(pl->d_table, pl->d_table_tf32, n, 0) != 0 || cudaStreamSynchronize(0) != cudaSuccess) {
+    cudaFree(pl->d_table_tf32);
+    pl->d_table_tf32 = nullptr;
+    return -1;
+  }
+  return 0;
 }
-void umma_plan_destroy(Plan*) {}
+void umma_plan_destroy(Plan* pl) {
+  if (pl->d_table_tf32) cudaFree(pl->d_table_tf32);
+  pl->d_table_tf32 = nullptr;
+}
 
 constexpr size_t kSmemMax = 232448 - 2048;  // 227 KB minus barriers / alignment slack
 
@@ -576,7 +591,7 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
   {
     long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
     int bx[3] = {32, 128, 1};
-    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx);
+    int rc = make_tmap(&p.tmA, pl->d_table_tf32, 3, d, s, bx);
     if (rc) return rc;
   }
   {
@@ -604,7 +619,7 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   {
     long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
     int bx[3] = {32, 32, 1};
-    int rc = make_tmap(&p.tmA, pl->d_table, 3, d, s, bx, true);
+    int rc = make_tmap(&p.tmA, pl->d_table_tf32, 3, d, s, bx, true);
     if (rc) return rc;
   }
   {

@@ -125,7 +125,7 @@ class _AnalysisPacked(torch.autograd.Function):
         lat = torch.empty(plan.latspec_elems(B, C), dtype=torch.float32, device=dev)
         spec = torch.empty(plan.spec_elems(B, C), dtype=torch.float32, device=dev)
         st = _stream(dev)
-        _lib.call("b200sht_fft_analysis", plan.handle, _ptr(x), _dtype_code(x.dtype), B, C, _ptr(lat), 0, st)
+        _lib.call("b200sht_fft_analysis", plan.handle, _ptr(x), _dtype_code(x.dtype), B, C, _ptr(lat), 0 | (2 if precision == _lib.PREC_TF32 else 0), st)
         _lib.call("b200sht_legendre_analysis", plan.handle, _ptr(lat), _ptr(spec), B, C, precision, st)
         ctx.plan, ctx.precision, ctx.shape, ctx.dtype = plan, precision, tuple(x.shape), x.dtype
         return spec
@@ -171,7 +171,7 @@ class _SynthesisPacked(torch.autograd.Function):
         dev = gy.device
         lat = torch.empty(plan.latspec_elems(B, C), dtype=torch.float32, device=dev)
         st = _stream(dev)
-        _lib.call("b200sht_fft_analysis", plan.handle, _ptr(gy), _dtype_code(gy.dtype), B, C, _ptr(lat), 1, st)
+        _lib.call("b200sht_fft_analysis", plan.handle, _ptr(gy), _dtype_code(gy.dtype), B, C, _ptr(lat), 1 | (2 if ctx.precision == _lib.PREC_TF32 else 0), st)
         gbias = None
         if ctx.has_bias and ctx.needs_input_grad[1]:
             gb = torch.empty(C, dtype=torch.float32, device=dev)

@@ -40,14 +40,14 @@ class PackedWeightCache:
         self._key = None
         self._packed = None
 
-    def get(self, w, op, L, M, G, Ci, Co):
-        key = (w.data_ptr(), w._version, w.device, op, L, G, Ci, Co)
+    def get(self, w, op, L, M, G, Ci, Co, precision=0):
+        key = (w.data_ptr(), w._version, w.device, op, L, G, Ci, Co, precision)
         if self.enabled and self._key == key and self._packed is not None:
             return self._packed
         n = int(_lib.load().b200sht_mix_weight_elems(op, L, M, G, Ci, Co))
         packed = torch.empty(n, dtype=torch.float32, device=w.device)
         wc = w.detach().contiguous()
-        _lib.call("b200sht_mix_weight_pack", op, _ptr(wc), _ptr(packed), L, G, Ci, Co, _stream(w.device))
+        _lib.call("b200sht_mix_weight_pack", op, _ptr(wc), _ptr(packed), L, G, Ci, Co, precision, _stream(w.device))
         self._key, self._packed = key, packed
         return packed
 
@@ -62,7 +62,7 @@ class _MixPacked(torch.autograd.Function):
         if weight.dtype != torch.complex64:
             raise B200ShtError(f"spectral weights must be complex64, got {weight.dtype}")
         if op in _DENSE_OPS:
-            wdev = cache.get(weight, op, L, M, G, Ci, Co) if cache is not None else PackedWeightCache().get(weight, op, L, M, G, Ci, Co)
+            wdev = (cache if cache is not None else PackedWeightCache()).get(weight, op, L, M, G, Ci, Co, precision)
         else:
             wdev = weight.detach().contiguous()
         y = torch.empty(int(_lib.load().b200sht_spec_elems_lm(L, M, B, Co)), dtype=torch.float32, device=dev)

@@ -85,7 +85,7 @@ def run_one(kernel, case):
         op = _lib.OP_DHCONV
         wn = torch.randn(G, Ci // G, Co // G, L, dtype=torch.complex64, device=dev)
         wp = torch.empty(int(lib.b200sht_mix_weight_elems(op, L, M, G, Ci, Co)), device=dev)
-        _lib.call("b200sht_mix_weight_pack", op, _ptr(wn), _ptr(wp), L, G, Ci, Co, st)
+        _lib.call("b200sht_mix_weight_pack", op, _ptr(wn), _ptr(wp), L, G, Ci, Co, 0, st)
         x, un = spec_rand(Ci)
         gy, _ = spec_rand(Co)
         outs = []
