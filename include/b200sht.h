@@ -64,6 +64,9 @@ typedef enum {
   B200SHT_OP_LDEP = 5         /* weight [L][Ci][Co]           contractions.py:106 (compl_exp_mul2d_fwd) */
 } b200sht_mix_op;
 
+/* or-ed into `op` (mix) / `mode` (ComplexReLU): the packed spec operands store every (l, m) entry (no block triangle) */
+#define B200SHT_DENSE_FLAG 0x100
+
 typedef struct b200sht_plan b200sht_plan;
 
 const char* b200sht_last_error(void);
@@ -75,8 +78,13 @@ int b200sht_version(void);
  * and stored as fp32 [mmax][lmax][kp]. */
 int b200sht_plan_create(b200sht_plan** plan, int nlat, int nlon, int lmax, int mmax,
                         const double* cost, const double* quad_w, int csphase, void* stream);
+/* Extended creation for the h x w model-parallel (distributed) SHT:
+ *   m_offset : the plan's orders are m_offset .. m_offset + mmax - 1 (this rank's shard of the orders)
+ *   flags & 1: FFT-only plan (no Legendre table): nlat is this rank's latitude count, quad_w its slice of the weights */
+int b200sht_plan_create_ex(b200sht_plan** plan, int nlat, int nlon, int lmax, int mmax, int m_offset, int flags,
+                           const double* cost, const double* quad_w, int csphase, void* stream);
 int b200sht_plan_destroy(b200sht_plan* plan);
-/* what: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 path available (0/1) */
+/* what: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 path available (0/1), 7 m_offset */
 int64_t b200sht_plan_query(const b200sht_plan* plan, int what);
 /* device pointer to the fp32 table [mmax][lmax][kp] (for tests) */
 const float* b200sht_plan_table(const b200sht_plan* plan);
@@ -111,6 +119,12 @@ int b200sht_legendre_synthesis(const b200sht_plan* plan, const float* spec, floa
  * mix / ComplexReLU entry points below depend only on the mode counts (L, M), not on a grid, so they take no plan. */
 int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream);
 int b200sht_spec_pack(int L, int M, const void* coeffs, float* spec, int B, int C, void* stream);
+/* same with an order offset (orders m_offset + m) and/or dense storage (every (l, m) entry stored: used for l/m-sharded spectra) */
+int b200sht_spec_unpack_ex(int L, int M, int m_offset, int dense, const float* spec, void* coeffs, int B, int C, void* stream);
+int b200sht_spec_pack_ex(int L, int M, int m_offset, int dense, const void* coeffs, float* spec, int B, int C, void* stream);
+/* latspec [mmax][2][B*C][kp] <-> complex64 [B*C][nlat][mmax]: the layout the distributed lat<->lon transposes exchange */
+int b200sht_latspec_unpack(const b200sht_plan* plan, const float* latspec, void* coeffs, int B, int C, void* stream);
+int b200sht_latspec_pack(const b200sht_plan* plan, const void* coeffs, float* latspec, int B, int C, void* stream);
 
 /* ------------------------------------------------------------------------- torch-harmonics boundary */
 /* bytes of scratch the four calls below need for (B, C) */

@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(_HERE, "..", "include", "b200sht.h")
 F32, BF16 = 0, 1
 PREC_FP32, PREC_TF32 = 0, 1
 OP_DHCONV, OP_DIAGONAL, OP_SEP_DHCONV, OP_SEP_DIAGONAL, OP_SHARED, OP_LDEP = range(6)
+DENSE_FLAG = 0x100
 
 
 class B200ShtError(RuntimeError):
@@ -30,6 +31,7 @@ _SIGNATURES = {
     "b200sht_last_error": (ctypes.c_char_p, []),
     "b200sht_version": (c_int, []),
     "b200sht_plan_create": (c_int, [ctypes.POINTER(_P), c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
+    "b200sht_plan_create_ex": (c_int, [ctypes.POINTER(_P), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P]),
     "b200sht_plan_destroy": (c_int, [_P]),
     "b200sht_plan_query": (c_int64, [_P, c_int]),
     "b200sht_plan_table": (_P, [_P]),
@@ -43,6 +45,10 @@ _SIGNATURES = {
     "b200sht_legendre_synthesis": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200sht_spec_unpack": (c_int, [c_int, c_int, _P, _P, c_int, c_int, _P]),
     "b200sht_spec_pack": (c_int, [c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "b200sht_spec_unpack_ex": (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "b200sht_spec_pack_ex": (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "b200sht_latspec_unpack": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "b200sht_latspec_pack": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "b200sht_sht_workspace_bytes": (c_int64, [_P, c_int, c_int]),
     "b200sht_sht_forward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
     "b200sht_sht_inverse": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),

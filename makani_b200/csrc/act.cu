@@ -9,7 +9,7 @@ __device__ __forceinline__ float dleaky(float x, float s) { return x > 0.f ? 1.f
 
 template <bool BWD>
 __global__ void complex_relu_kernel(int mode, const float* __restrict__ x, const float* __restrict__ bias, float slope, const float* __restrict__ gy,
-                                    float* __restrict__ out, float* __restrict__ gbias, int L, int M, int B, int C, int cp) {
+                                    float* __restrict__ out, float* __restrict__ gbias, int L, int M, int B, int C, int cp, int dense) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)L * M * B * cp;
   if (idx >= total) return;
@@ -18,7 +18,7 @@ __global__ void complex_relu_kernel(int mode, const float* __restrict__ x, const
   const int b = (int)(rest % B); rest /= B;
   const int m = (int)(rest % M);
   const int l = (int)(rest / M);
-  if (m >= mend(l, M)) return;
+  if (m >= mend_d(l, M, dense)) return;
   const size_t base = ((size_t)l * M + m) * 2 * B * cp + (size_t)b * cp + c;
   const size_t plane = (size_t)B * cp;
   if (c >= C) {  // keep the channel padding at zero
@@ -67,7 +67,7 @@ int complex_relu_fwd(const Plan* pl, int mode, const float* x, const float* bias
   B200_REQUIRE(mode >= 0 && mode <= 3, "complex_relu: unknown mode %d", mode);
   const int cp = round_up(C, 4);
   const long long total = (long long)pl->lmax * pl->mmax * B * cp;
-  complex_relu_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mode, x, bias, slope, nullptr, y, nullptr, pl->lmax, pl->mmax, B, C, cp);
+  complex_relu_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mode, x, bias, slope, nullptr, y, nullptr, pl->lmax, pl->mmax, B, C, cp, pl->dense);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -78,7 +78,7 @@ int complex_relu_bwd(const Plan* pl, int mode, const float* x, const float* bias
   const int cp = round_up(C, 4);
   const long long total = (long long)pl->lmax * pl->mmax * B * cp;
   if (gbias) B200_CHECK_CUDA(cudaMemsetAsync(gbias, 0, sizeof(float) * C, st));
-  complex_relu_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mode, x, bias, slope, gy, gx, gbias, pl->lmax, pl->mmax, B, C, cp);
+  complex_relu_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mode, x, bias, slope, gy, gx, gbias, pl->lmax, pl->mmax, B, C, cp, pl->dense);
   B200_CHECK_LAUNCH();
   return 0;
 }

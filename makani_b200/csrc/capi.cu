@@ -48,7 +48,8 @@ int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, con
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static inline int cp_of(int C) { return round_up(C, 4); }
 // dims-only plan for the entry points that depend on (L, M) alone
-static inline Plan lm_plan(int L, int M) { Plan p; memset(&p, 0, sizeof(p)); p.lmax = L; p.mmax = M; return p; }
+static inline Plan lm_plan(int L, int M, int m0 = 0, int dense = 0) { Plan p; memset(&p, 0, sizeof(p)); p.lmax = L; p.mmax = M; p.m0 = m0; p.dense = dense; return p; }
+int latspec_convert(const Plan* pl, float* lat, void* coeffs, int B, int C, int to_packed, cudaStream_t st);
 int umma_available();
 
 }  // namespace b200sht
@@ -62,12 +63,19 @@ int b200sht_version(void) { return 100; }
 
 int b200sht_plan_create(b200sht_plan** out, int nlat, int nlon, int lmax, int mmax, const double* cost, const double* quad_w, int csphase,
                         void* stream) {
+  return b200sht_plan_create_ex(out, nlat, nlon, lmax, mmax, 0, 0, cost, quad_w, csphase, stream);
+}
+
+int b200sht_plan_create_ex(b200sht_plan** out, int nlat, int nlon, int lmax, int mmax, int m_offset, int flags, const double* cost,
+                           const double* quad_w, int csphase, void* stream) {
   B200_REQUIRE(out != nullptr && cost != nullptr && quad_w != nullptr, "plan_create: null argument");
-  B200_REQUIRE(nlat >= 2 && nlon >= 2 && lmax >= 1 && mmax >= 1, "plan_create: bad sizes nlat=%d nlon=%d lmax=%d mmax=%d", nlat, nlon, lmax, mmax);
-  B200_REQUIRE(mmax <= nlon / 2 + 1, "plan_create: mmax=%d exceeds nlon/2+1=%d", mmax, nlon / 2 + 1);
+  B200_REQUIRE(nlat >= 1 && nlon >= 2 && lmax >= 1 && mmax >= 1 && m_offset >= 0, "plan_create: bad sizes nlat=%d nlon=%d lmax=%d mmax=%d m_offset=%d", nlat,
+               nlon, lmax, mmax, m_offset);
+  B200_REQUIRE(m_offset + mmax <= nlon / 2 + 1, "plan_create: m_offset+mmax=%d exceeds nlon/2+1=%d", m_offset + mmax, nlon / 2 + 1);
   b200sht_plan* pl = new b200sht_plan();
   memset(static_cast<Plan*>(pl), 0, sizeof(Plan));
   pl->nlat = nlat; pl->nlon = nlon; pl->lmax = lmax; pl->mmax = mmax; pl->kp = round_up(nlat, 8); pl->csphase = csphase;
+  pl->m0 = m_offset; pl->no_table = (flags & 1) ? 1 : 0;
   if (!make_fft_plan(nlon, &pl->fft)) {
     set_error("plan_create: nlon=%d has a prime factor > 13 (unsupported FFT length)", nlon);
     delete pl;
@@ -77,7 +85,7 @@ int b200sht_plan_create(b200sht_plan** out, int nlat, int nlon, int lmax, int mm
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
-  const size_t tbytes = sizeof(float) * (size_t)mmax * lmax * pl->kp;
+  const size_t tbytes = pl->no_table ? 16 : sizeof(float) * (size_t)mmax * lmax * pl->kp;
   double* d_cost = nullptr;
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_table, tbytes);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_rowscale, sizeof(float) * pl->kp);
@@ -101,7 +109,7 @@ int b200sht_plan_create(b200sht_plan** out, int nlat, int nlon, int lmax, int mm
     if ((e = cudaMemcpyAsync(pl->d_rowscale, rs.data(), sizeof(float) * pl->kp, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
     if ((e = cudaMemcpyAsync(pl->d_twiddle, tw.data(), sizeof(float2) * nlon, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
     if ((e = cudaMemcpyAsync(d_cost, cost, sizeof(double) * nlat, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-    rc = build_table(pl, d_cost, st);
+    if (!pl->no_table) rc = build_table(pl, d_cost, st);
     if (rc) break;
     // host staging vectors go out of scope: wait for the copies (plan creation is not on the hot path)
     e = cudaStreamSynchronize(st);
@@ -113,7 +121,7 @@ int b200sht_plan_create(b200sht_plan** out, int nlat, int nlon, int lmax, int mm
     delete pl;
     return rc ? rc : B200SHT_ERR_CUDA;
   }
-  pl->umma_ok = (umma_plan_init(pl) == 0) ? 1 : 0;
+  pl->umma_ok = (!pl->no_table && umma_plan_init(pl) == 0) ? 1 : 0;
   *out = pl;
   return 0;
 }
@@ -138,6 +146,7 @@ int64_t b200sht_plan_query(const b200sht_plan* pl, int what) {
     case 4: return pl->kp;
     case 5: return (int64_t)sizeof(float) * pl->mmax * pl->lmax * pl->kp;
     case 6: return pl->umma_ok;
+    case 7: return pl->m0;
     default: return -1;
   }
 }
@@ -182,6 +191,7 @@ static int check_precision(int umma_ok, int precision, const char* who) {
 
 int b200sht_legendre_analysis(const b200sht_plan* pl, const float* latspec, float* spec, int B, int C, int precision, void* stream) {
   B200_REQUIRE(pl && latspec && spec && B > 0 && C > 0, "legendre_analysis: bad argument");
+  B200_REQUIRE(!pl->no_table, "legendre_analysis: FFT-only plan");
   int rc = check_precision(pl->umma_ok, precision, "legendre_analysis");
   if (rc) return rc;
   return precision == B200SHT_PREC_TF32 ? legendre_analysis_umma(pl, latspec, spec, B, C, S(stream))
@@ -190,6 +200,7 @@ int b200sht_legendre_analysis(const b200sht_plan* pl, const float* latspec, floa
 
 int b200sht_legendre_synthesis(const b200sht_plan* pl, const float* spec, float* latspec, int B, int C, int precision, void* stream) {
   B200_REQUIRE(pl && latspec && spec && B > 0 && C > 0, "legendre_synthesis: bad argument");
+  B200_REQUIRE(!pl->no_table, "legendre_synthesis: FFT-only plan");
   int rc = check_precision(pl->umma_ok, precision, "legendre_synthesis");
   if (rc) return rc;
   return precision == B200SHT_PREC_TF32 ? legendre_synthesis_umma(pl, spec, latspec, B, C, S(stream))
@@ -205,6 +216,25 @@ int b200sht_spec_pack(int L, int M, const void* coeffs, float* spec, int B, int 
   B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_pack: bad argument");
   Plan p = lm_plan(L, M);
   return spec_pack(&p, coeffs, spec, B, C, S(stream));
+}
+
+int b200sht_spec_unpack_ex(int L, int M, int m_offset, int dense, const float* spec, void* coeffs, int B, int C, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_unpack: bad argument");
+  Plan p = lm_plan(L, M, m_offset, dense);
+  return spec_unpack(&p, spec, coeffs, B, C, S(stream));
+}
+int b200sht_spec_pack_ex(int L, int M, int m_offset, int dense, const void* coeffs, float* spec, int B, int C, void* stream) {
+  B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_pack: bad argument");
+  Plan p = lm_plan(L, M, m_offset, dense);
+  return spec_pack(&p, coeffs, spec, B, C, S(stream));
+}
+int b200sht_latspec_unpack(const b200sht_plan* pl, const float* latspec, void* coeffs, int B, int C, void* stream) {
+  B200_REQUIRE(pl && latspec && coeffs, "latspec_unpack: null argument");
+  return latspec_convert(pl, const_cast<float*>(latspec), coeffs, B, C, 0, S(stream));
+}
+int b200sht_latspec_pack(const b200sht_plan* pl, const void* coeffs, float* latspec, int B, int C, void* stream) {
+  B200_REQUIRE(pl && latspec && coeffs, "latspec_pack: null argument");
+  return latspec_convert(pl, latspec, const_cast<void*>(coeffs), B, C, 1, S(stream));
 }
 
 int b200sht_bias_grad(const b200sht_plan* pl, const float* latspec, float* gbias, int B, int C, void* stream) {
@@ -302,7 +332,8 @@ int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, con
   B200_REQUIRE(L > 0 && M > 0 && x && w && y, "mix_forward: bad argument");
   int rc = check_precision(umma_available(), precision, "mix_forward");
   if (rc) return rc;
-  Plan p = lm_plan(L, M);
+  Plan p = lm_plan(L, M, 0, (op & kDenseFlag) ? 1 : 0);
+  op &= 0xff;
   const Plan* pl = &p;
   if (precision == B200SHT_PREC_TF32 && dense_op(op) && umma_mix_shape(B, G, Ci, Co)) return mix_forward_umma(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));
   return mix_forward_simt(pl, op, x, w, cbias, y, B, G, Ci, Co, S(stream));  // per-mode operators are bandwidth bound: one path
@@ -314,7 +345,8 @@ int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, co
   B200_REQUIRE(gw == nullptr || x != nullptr, "mix_backward: weight gradient needs x");
   int rc = check_precision(umma_available(), precision, "mix_backward");
   if (rc) return rc;
-  Plan p = lm_plan(L, M);
+  Plan p = lm_plan(L, M, 0, (op & kDenseFlag) ? 1 : 0);
+  op &= 0xff;
   const Plan* pl = &p;
   if (precision == B200SHT_PREC_TF32 && dense_op(op) && umma_mix_shape(B, G, Ci, Co)) return mix_backward_umma(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
   return mix_backward_simt(pl, op, x, w, gy, gx, gw, gcbias, B, G, Ci, Co, S(stream));
@@ -323,13 +355,15 @@ int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, co
 int b200sht_complex_relu_forward(int L, int M, int mode, const float* x, const float* bias, float slope, float* y, int B, int C,
                                  void* stream) {
   B200_REQUIRE(L > 0 && M > 0 && x && y, "complex_relu_forward: bad argument");
-  Plan p = lm_plan(L, M);
+  Plan p = lm_plan(L, M, 0, (mode & kDenseFlag) ? 1 : 0);
+  mode &= 0xff;
   return complex_relu_fwd(&p, mode, x, bias, slope, y, B, C, S(stream));
 }
 int b200sht_complex_relu_backward(int L, int M, int mode, const float* x, const float* bias, float slope, const float* gy, float* gx,
                                   float* gbias, int B, int C, void* stream) {
   B200_REQUIRE(L > 0 && M > 0 && x && gy && gx, "complex_relu_backward: bad argument");
-  Plan p = lm_plan(L, M);
+  Plan p = lm_plan(L, M, 0, (mode & kDenseFlag) ? 1 : 0);
+  mode &= 0xff;
   return complex_relu_bwd(&p, mode, x, bias, slope, gy, gx, gbias, B, C, S(stream));
 }
 

@@ -48,6 +48,9 @@ HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
 constexpr int kTriBlock = 32;
 HD int lstart(int m) { return (m / kTriBlock) * kTriBlock; }
 HD int mend(int l, int M) { int e = (l / kTriBlock + 1) * kTriBlock; return e < M ? e : M; }
+// `dense` storage (used for the l/m-sharded spectra of the h x w model-parallel path): every (l, m) entry is stored
+HD int mend_d(int l, int M, int dense) { return dense ? M : mend(l, M); }
+constexpr int kDenseFlag = 0x100;  // or-ed into the `op` / `mode` argument of the mix / ComplexReLU entry points
 
 struct FftPlan {
   int N;
@@ -59,6 +62,9 @@ struct FftPlan {
 struct Plan {
   int nlat, nlon, lmax, mmax, kp;
   int csphase;
+  int m0;               // global order of local order 0 (m-sharded plans of the distributed SHT); 0 otherwise
+  int no_table;         // FFT-only plan (latitude-sharded stage of the distributed SHT)
+  int dense;            // dims-only plans: packed spec tensors store every (l, m) entry (no block triangle)
   float* d_table;       // [mmax][lmax][kp]
   float* d_table_tf32;  // same, rounded to nearest TF32 (operand of the tcgen05 kernels); null when that path is unavailable
   float* d_rowscale;    // [kp]  quad_w[k] * 2 pi / nlon (0 in the padding)

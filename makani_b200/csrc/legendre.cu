@@ -50,7 +50,7 @@ int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st) {
 }
 
 __global__ void build_table_kernel(float* __restrict__ table, const double* __restrict__ cost, int nlat, int kp, int lmax,
-                                   int mmax, int csphase) {
+                                   int mmax, int csphase, int m0) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (k >= kp) return;
@@ -59,12 +59,12 @@ __global__ void build_table_kernel(float* __restrict__ table, const double* __re
     for (int l = 0; l < lmax; ++l) out[(size_t)l * kp] = 0.f;
     return;
   }
-  legendre_column(m, lmax, cost[k], csphase, out, kp);
+  legendre_column(m0 + m, lmax, cost[k], csphase, out, kp);
 }
 
 int build_table(Plan* pl, const double* d_cost, cudaStream_t st) {
   dim3 grid(ceil_div(pl->kp, 128), pl->mmax);
-  build_table_kernel<<<grid, 128, 0, st>>>(pl->d_table, d_cost, pl->nlat, pl->kp, pl->lmax, pl->mmax, pl->csphase);
+  build_table_kernel<<<grid, 128, 0, st>>>(pl->d_table, d_cost, pl->nlat, pl->kp, pl->lmax, pl->mmax, pl->csphase, pl->m0);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -84,11 +84,11 @@ constexpr int TK = 16;   // k slab
 // spec[l][m][jp] = sum_k P[m][l][k] * X[m][j][k]      grid: (jp tiles, l tiles, m)
 __global__ void __launch_bounds__(256) legendre_analysis_simt_kernel(const float* __restrict__ P, const float* __restrict__ X,
                                                                      float* __restrict__ spec, int L, int M, int kp, int B,
-                                                                     int C, int cp) {
+                                                                     int C, int cp, int m0) {
   __shared__ float As[TK][TS + 4];
   __shared__ float Bs[TK][TS + 4];
   const int m = blockIdx.z;
-  const int l0 = lstart(m) + blockIdx.y * TS;
+  const int l0 = lstart(m0 + m) + blockIdx.y * TS;
   if (l0 >= L) return;
   const int JP = 2 * B * cp, J = 2 * B * C;
   const int jp0 = blockIdx.x * TS;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) legendre_analysis_simt_kernel(const float
 // Z[m][j][k] = sum_{l >= lstart(m)} P[m][l][k] * spec[l][m][jp]     grid: (jp tiles, k tiles, m)
 __global__ void __launch_bounds__(256) legendre_synthesis_simt_kernel(const float* __restrict__ P, const float* __restrict__ spec,
                                                                       float* __restrict__ Z, int L, int M, int kp, int B, int C,
-                                                                      int cp) {
+                                                                      int cp, int m0) {
   __shared__ float As[TK][TS + 4];  // [l][k]
   __shared__ float Bs[TK][TS + 4];  // [l][jp]
   const int m = blockIdx.z;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) legendre_synthesis_simt_kernel(const floa
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int l0 = lstart(m); l0 < L; l0 += TK) {
+  for (int l0 = lstart(m0 + m); l0 < L; l0 += TK) {
     const int l = l0 + lrow;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (l < L) {
@@ -202,7 +202,7 @@ int legendre_analysis_simt(const Plan* pl, const float* X, float* spec, int B, i
   const int cp = round_up(C, 4);
   const int JP = 2 * B * cp;
   dim3 grid(ceil_div(JP, TS), ceil_div(pl->lmax, TS), pl->mmax);
-  legendre_analysis_simt_kernel<<<grid, 256, 0, st>>>(pl->d_table, X, spec, pl->lmax, pl->mmax, pl->kp, B, C, cp);
+  legendre_analysis_simt_kernel<<<grid, 256, 0, st>>>(pl->d_table, X, spec, pl->lmax, pl->mmax, pl->kp, B, C, cp, pl->m0);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -211,7 +211,7 @@ int legendre_synthesis_simt(const Plan* pl, const float* spec, float* Z, int B, 
   const int cp = round_up(C, 4);
   const int JP = 2 * B * cp;
   dim3 grid(ceil_div(JP, TS), ceil_div(pl->kp, TS), pl->mmax);
-  legendre_synthesis_simt_kernel<<<grid, 256, 0, st>>>(pl->d_table, spec, Z, pl->lmax, pl->mmax, pl->kp, B, C, cp);
+  legendre_synthesis_simt_kernel<<<grid, 256, 0, st>>>(pl->d_table, spec, Z, pl->lmax, pl->mmax, pl->kp, B, C, cp, pl->m0);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -219,7 +219,7 @@ int legendre_synthesis_simt(const Plan* pl, const float* spec, float* Z, int B, 
 // -------------------------------------------------------------------------------- pack / unpack
 // spec [L][M][2][B][cp]  <->  coeffs complex64 [B*C][L][M].   block: 32 m x 32 c tile of one (l, b)
 __global__ void __launch_bounds__(256) spec_unpack_kernel(const float* __restrict__ spec, float2* __restrict__ coeffs, int L, int M,
-                                                          int B, int C, int cp) {
+                                                          int B, int C, int cp, int mo, int dense) {
   __shared__ float tile[2][32][33];
   const int l = blockIdx.z / B, b = blockIdx.z % B;
   const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) spec_unpack_kernel(const float* __restric
   for (int mm = ty; mm < 32; mm += 8) {
     const int m = m0 + mm, c = c0 + tx;
     float re = 0.f, im = 0.f;
-    if (m < M && c < C && l >= m) {  // exact zeros for l < m
+    if (m < M && c < C && (dense || l >= mo + m)) {  // exact zeros for l < m (global order mo + m)
       const float* row = spec + ((size_t)l * M + m) * JP;
       re = row[(0 * B + b) * cp + c];
       im = row[(1 * B + b) * cp + c];
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) spec_unpack_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) spec_pack_kernel(const float2* __restrict__ coeffs, float* __restrict__ spec, int L, int M, int B,
-                                                        int C, int cp) {
+                                                        int C, int cp, int mo, int dense) {
   __shared__ float tile[2][32][33];
   const int l = blockIdx.z / B, b = blockIdx.z % B;
   const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // c0 runs over cp
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) spec_pack_kernel(const float2* __restrict
   __syncthreads();
   for (int mm = ty; mm < 32; mm += 8) {
     const int m = m0 + mm, c = c0 + tx;
-    if (m < M && c < cp && l >= lstart(m)) {
+    if (m < M && c < cp && (dense || l >= lstart(mo + m))) {
       float* row = spec + ((size_t)l * M + m) * JP;
       row[(0 * B + b) * cp + c] = tile[0][mm][tx];
       row[(1 * B + b) * cp + c] = tile[1][mm][tx];
@@ -272,7 +272,7 @@ int spec_unpack(const Plan* pl, const float* spec, void* coeffs, int B, int C, c
   const int cp = round_up(C, 4);
   dim3 grid(ceil_div(pl->mmax, 32), ceil_div(C, 32), pl->lmax * B);
   B200_REQUIRE(grid.z <= 65535, "spec_unpack: lmax*B=%u exceeds grid limit", grid.z);
-  spec_unpack_kernel<<<grid, 256, 0, st>>>(spec, static_cast<float2*>(coeffs), pl->lmax, pl->mmax, B, C, cp);
+  spec_unpack_kernel<<<grid, 256, 0, st>>>(spec, static_cast<float2*>(coeffs), pl->lmax, pl->mmax, B, C, cp, pl->m0, pl->dense);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -281,7 +281,57 @@ int spec_pack(const Plan* pl, const void* coeffs, float* spec, int B, int C, cud
   const int cp = round_up(C, 4);
   dim3 grid(ceil_div(pl->mmax, 32), ceil_div(cp, 32), pl->lmax * B);
   B200_REQUIRE(grid.z <= 65535, "spec_pack: lmax*B=%u exceeds grid limit", grid.z);
-  spec_pack_kernel<<<grid, 256, 0, st>>>(static_cast<const float2*>(coeffs), spec, pl->lmax, pl->mmax, B, C, cp);
+  spec_pack_kernel<<<grid, 256, 0, st>>>(static_cast<const float2*>(coeffs), spec, pl->lmax, pl->mmax, B, C, cp, pl->m0, pl->dense);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// latspec [M][2][R][kp]  <->  complex64 [R][nlat][M]   (the layout the distributed transposes exchange).  block: 32 k x 32 m of one row r
+__global__ void __launch_bounds__(256) latspec_convert_kernel(float* __restrict__ lat, float2* __restrict__ coeffs, int M, int R, int nlat, int kp,
+                                                              int to_packed) {
+  __shared__ float tile[2][32][33];
+  const int r = blockIdx.z;
+  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (!to_packed) {
+    for (int mm = ty; mm < 32; mm += 8) {
+      const int m = m0 + mm, k = k0 + tx;
+      float re = 0.f, im = 0.f;
+      if (m < M && k < nlat) {
+        re = lat[(((size_t)m * 2 + 0) * R + r) * kp + k];
+        im = lat[(((size_t)m * 2 + 1) * R + r) * kp + k];
+      }
+      tile[0][mm][tx] = re;
+      tile[1][mm][tx] = im;
+    }
+    __syncthreads();
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk, m = m0 + tx;
+      if (k < nlat && m < M) coeffs[((size_t)r * nlat + k) * M + m] = make_float2(tile[0][tx][kk], tile[1][tx][kk]);
+    }
+  } else {
+    for (int kk = ty; kk < 32; kk += 8) {
+      const int k = k0 + kk, m = m0 + tx;
+      float2 v = make_float2(0.f, 0.f);
+      if (k < nlat && m < M) v = coeffs[((size_t)r * nlat + k) * M + m];
+      tile[0][tx][kk] = v.x;
+      tile[1][tx][kk] = v.y;
+    }
+    __syncthreads();
+    for (int mm = ty; mm < 32; mm += 8) {
+      const int m = m0 + mm, k = k0 + tx;
+      if (m < M && k < kp) {  // the k padding is written as zeros
+        lat[(((size_t)m * 2 + 0) * R + r) * kp + k] = tile[0][mm][tx];
+        lat[(((size_t)m * 2 + 1) * R + r) * kp + k] = tile[1][mm][tx];
+      }
+    }
+  }
+}
+
+int latspec_convert(const Plan* pl, float* lat, void* coeffs, int B, int C, int to_packed, cudaStream_t st) {
+  dim3 grid(ceil_div(pl->kp, 32), ceil_div(pl->mmax, 32), B * C);
+  B200_REQUIRE(grid.z <= 65535, "latspec_convert: B*C=%u exceeds grid limit", grid.z);
+  latspec_convert_kernel<<<grid, 256, 0, st>>>(lat, static_cast<float2*>(coeffs), pl->mmax, B * C, pl->nlat, pl->kp, to_packed);
   B200_CHECK_LAUNCH();
   return 0;
 }

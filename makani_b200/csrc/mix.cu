@@ -15,6 +15,7 @@ struct MixDims {
   int cpi, cpo;               // padded total channel counts of the in / out spec tensors
   int cop;                    // padded Cog in the packed weight (planar: float [L][G][Cig][2][cop])
   long long wl_stride;        // floats between consecutive l in the packed weight (0: shared)
+  int dense;                  // spec tensors store every (l, m) entry (l/m-sharded spectra of the distributed path)
 };
 
 // ------------------------------------------------------------------------------------ weight re-layout
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) mix_dense_kernel(const float* __restrict_
                                                         float* __restrict__ yout, const MixDims d) {
   __shared__ float Xr[16][33], Xi[16][33], Wr[16][33], Wi[16][33];
   const int l = blockIdx.z;
-  const int nrows = mend(l, d.M) * d.B;
+  const int nrows = mend_d(l, d.M, d.dense) * d.B;
   const int row0 = blockIdx.x * 32;
   if (row0 >= nrows) return;
   const int K = MODE == 0 ? d.Cig : d.Cog;          // contraction length
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) mix_wgrad_kernel(const float* __restrict_
   float ar[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, ai[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   const int lbeg = shared_w ? 0 : blockIdx.z, lend = shared_w ? d.L : blockIdx.z + 1;
   for (int l = lbeg; l < lend; ++l) {
-    const int nrows = mend(l, d.M) * d.B;
+    const int nrows = mend_d(l, d.M, d.dense) * d.B;
     for (int r0 = 0; r0 < nrows; r0 += 16) {
       const int row = r0 + lrow;
       float x0r = 0.f, x0i = 0.f, x1r = 0.f, x1i = 0.f, g0r = 0.f, g0i = 0.f, g1r = 0.f, g1i = 0.f;
@@ -265,11 +266,11 @@ __global__ void __launch_bounds__(256) mix_wgrad_kernel(const float* __restrict_
 }
 
 // complex bias gradient (OP_SHARED / OP_LDEP): gcb[o] = sum over the stored triangle and batch of gy[.., o]
-__global__ void mix_cbias_grad_kernel(const float* __restrict__ gy, float2* __restrict__ gcb, int L, int M, int B, int cpo) {
+__global__ void mix_cbias_grad_kernel(const float* __restrict__ gy, float2* __restrict__ gcb, int L, int M, int B, int cpo, int dense) {
   const int o = blockIdx.x;
   float sr = 0.f, si = 0.f;
   for (int l = 0; l < L; ++l) {
-    const int nrows = mend(l, M) * B;
+    const int nrows = mend_d(l, M, dense) * B;
     for (int row = threadIdx.x; row < nrows; row += blockDim.x) {
       const int m = row / B, b = row % B;
       const float* base = gy + ((size_t)l * M + m) * 2 * B * cpo + (size_t)b * cpo + o;
@@ -288,8 +289,8 @@ __global__ void mix_cbias_grad_kernel(const float* __restrict__ gy, float2* __re
   }
 }
 
-int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, cudaStream_t st) {
-  mix_cbias_grad_kernel<<<Co, 256, 0, st>>>(gy, static_cast<float2*>(gcb), L, M, B, round_up(Co, 4));
+int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, int dense, cudaStream_t st) {
+  mix_cbias_grad_kernel<<<Co, 256, 0, st>>>(gy, static_cast<float2*>(gcb), L, M, B, round_up(Co, 4), dense);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -310,7 +311,7 @@ __global__ void mix_permode_kernel(const float* __restrict__ xin, const float2* 
   const int l = (int)(rest % d.L); rest /= d.L;
   const int oc = (int)(rest % NOut);
   const int b = (int)(rest / NOut);
-  if (m >= mend(l, d.M)) return;
+  if (m >= mend_d(l, d.M, d.dense)) return;
   const int cp_in = MODE == 0 ? d.cpi : d.cpo, cp_out = MODE == 0 ? d.cpo : d.cpi;
   const float* xb = xin + ((size_t)l * d.M + m) * 2 * d.B * cp_in + (size_t)b * cp_in;
   const size_t xp = (size_t)d.B * cp_in;
@@ -351,7 +352,7 @@ __global__ void mix_permode_wgrad_kernel(const float* __restrict__ xin, const fl
   if (OP == B200SHT_OP_SEP_DHCONV) {
     const int l = (int)(idx % d.L);
     const int c = (int)(idx / d.L);
-    const int me = mend(l, d.M);
+    const int me = mend_d(l, d.M, d.dense);
     for (int m = 0; m < me; ++m)
       for (int b = 0; b < d.B; ++b) {
         const float* xb = xin + ((size_t)l * d.M + m) * 2 * d.B * d.cpi + (size_t)b * d.cpi + c;
@@ -370,7 +371,7 @@ __global__ void mix_permode_wgrad_kernel(const float* __restrict__ xin, const fl
       const int g = (int)(rest / d.Cig);
       ci = g * d.Cig + i; co = g * d.Cog + o;
     } else { ci = co = (int)rest; }
-    if (m < mend(l, d.M))
+    if (m < mend_d(l, d.M, d.dense))
       for (int b = 0; b < d.B; ++b) {
         const float* xb = xin + ((size_t)l * d.M + m) * 2 * d.B * d.cpi + (size_t)b * d.cpi + ci;
         const float* gb = gy + ((size_t)l * d.M + m) * 2 * d.B * d.cpo + (size_t)b * d.cpo + co;
@@ -386,6 +387,7 @@ static int make_dims(const Plan* pl, int op, int B, int G, int Ci, int Co, MixDi
   B200_REQUIRE(B > 0 && G > 0 && Ci > 0 && Co > 0 && Ci % G == 0 && Co % G == 0, "mix: bad dims B=%d G=%d Ci=%d Co=%d", B, G, Ci, Co);
   if (op == B200SHT_OP_SEP_DHCONV || op == B200SHT_OP_SEP_DIAGONAL) B200_REQUIRE(Ci == Co, "mix: separable operator needs Ci == Co");
   if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) B200_REQUIRE(G == 1, "mix: OP_SHARED/OP_LDEP are ungrouped");
+  d->dense = pl->dense;
   d->L = pl->lmax; d->M = pl->mmax; d->B = B; d->G = G; d->Cig = Ci / G; d->Cog = Co / G;
   d->cpi = round_up(Ci, 4); d->cpo = round_up(Co, 4); d->cop = round_up(Co / G, 4);
   d->wl_stride = (op == B200SHT_OP_SHARED) ? 0 : (long long)G * (Ci / G) * d->cop * 2;
@@ -437,7 +439,7 @@ int mix_backward_simt(const Plan* pl, int op, const float* x, const void* w, con
       B200_CHECK_LAUNCH();
     }
     if (gcbias) {
-      mix_cbias_grad_kernel<<<Co, 256, 0, st>>>(gy, static_cast<float2*>(gcbias), d.L, d.M, B, d.cpo);
+      mix_cbias_grad_kernel<<<Co, 256, 0, st>>>(gy, static_cast<float2*>(gcbias), d.L, d.M, B, d.cpo, d.dense);
       B200_CHECK_LAUNCH();
     }
   } else {

@@ -211,13 +211,13 @@ struct AnaTraits {
     alignas(64) CUtensorMap tmA;  // table  (k, l, m)       box (32, 128, 1)
     alignas(64) CUtensorMap tmB;  // X      (k, c, pb, m)   box (32, Cc, PBc, 1)
     float* spec;
-    int L, M, nlat, C, cp, PB, Cc, PBc, n_ct, N;
+    int L, M, nlat, C, cp, PB, Cc, PBc, n_ct, N, m0;
     uint32_t idesc;
   };
   struct Tile { int m, l0, c0, pb0; };
   __device__ static bool make_tile(const Params& p, Tile& t) {
     t.m = blockIdx.z;
-    t.l0 = lstart(t.m) + 128 * blockIdx.x;
+    t.l0 = lstart(p.m0 + t.m) + 128 * blockIdx.x;
     t.c0 = (blockIdx.y % p.n_ct) * p.Cc;
     t.pb0 = (blockIdx.y / p.n_ct) * p.PBc;
     return t.l0 < p.L;
@@ -260,7 +260,7 @@ struct SynTraits {
     alignas(64) CUtensorMap tmA;  // table (k, l, m)   box (32, 32, 1)   MN-major A (M = k)
     alignas(64) CUtensorMap tmB;  // spec  (n, m, l)   box (32, 1, 32)   MN-major B (N = n)
     float* Z;
-    int L, M, nlat, kp, C, cp, PB, nblk, N;
+    int L, M, nlat, kp, C, cp, PB, nblk, N, m0;
     uint32_t idesc;
   };
   struct Tile { int m, k0, n0, lbeg; };
@@ -268,7 +268,7 @@ struct SynTraits {
     t.m = blockIdx.z;
     t.k0 = 128 * blockIdx.x;
     t.n0 = p.N * blockIdx.y;
-    t.lbeg = lstart(t.m);
+    t.lbeg = lstart(p.m0 + t.m);
     return true;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
@@ -317,6 +317,7 @@ struct MixParams : EngineParams {
   int nblk, N;             // N = output columns per tile; nblk = N / 32 (MN-major B operands)
   int n_nt;                // output tiles per group
   int shared_w;            // weight has no l dimension
+  int dense;               // spec tensors store every (l, m) entry
   long long wl_stride;
   uint32_t idesc, idesc_neg;
   uint32_t offA_i, offB_r, offB_i;  // stage offsets of the imaginary A tile and the two B tiles (A_r at 0)
@@ -331,7 +332,7 @@ struct MixFwdTraits {
     t.g = blockIdx.y / p.n_nt;
     t.o0 = (blockIdx.y % p.n_nt) * p.N;
     t.lg = (p.shared_w ? 0 : t.l * p.G) + t.g;
-    return t.m0 < mend(t.l, p.M);
+    return t.m0 < mend_d(t.l, p.M, p.dense);
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmW); }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.Cig + 31) / 32; }
@@ -361,7 +362,7 @@ struct MixFwdTraits {
                                     bool with_bias) {
     const int r = warp * 32 + lane;
     const int m = m0 + r / p.B, b = r % p.B;
-    const bool row_ok = (r < p.Mt * p.B) && (m < mend(l, p.M));
+    const bool row_ok = (r < p.Mt * p.B) && (m < mend_d(l, p.M, p.dense));
     const int pad = cp_out - NOg * p.G;
     const int limit = NOg + ((g == p.G - 1) ? pad : 0);  // columns of this group incl. trailing zero padding
     float* yr = p.out + ((size_t)(row_ok ? l : 0) * p.M + (row_ok ? m : 0)) * 2 * p.B * cp_out + (size_t)b * cp_out + g * NOg;
@@ -430,7 +431,7 @@ struct MixWgradTraits {
     return true;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmX2); }
-  __device__ static int kb_of_l(const Params& p, int l) { return (mend(l, p.M) * p.B + 31) / 32; }
+  __device__ static int kb_of_l(const Params& p, int l) { return (mend_d(l, p.M, p.dense) * p.B + 31) / 32; }
   __device__ static int num_kblocks(const Params& p, const Tile& t) {
     if (!p.shared_w) return kb_of_l(p, t.lz);
     int n = 0;
@@ -582,7 +583,7 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
   AnaTraits::Params p;
   memset(&p, 0, sizeof(p));
   const int cp = round_up(C, 4), PB = 2 * B;
-  p.spec = spec; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.C = C; p.cp = cp; p.PB = PB;
+  p.spec = spec; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.C = C; p.cp = cp; p.PB = PB; p.m0 = pl->m0;
   if (cp <= 128) { p.Cc = cp; p.n_ct = 1; p.PBc = 256 / cp < PB ? 256 / cp : PB; }
   else { p.n_ct = ceil_div(cp, 128); p.Cc = round_up(ceil_div(cp, p.n_ct), 4); p.PBc = (2 * p.Cc <= 256 && PB >= 2) ? 2 : 1; }
   const int rows = p.Cc * p.PBc;
@@ -612,7 +613,7 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   SynTraits::Params p;
   memset(&p, 0, sizeof(p));
   const int cp = round_up(C, 4), PB = 2 * B, JP = PB * cp;
-  p.Z = Z; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.kp = pl->kp; p.C = C; p.cp = cp; p.PB = PB;
+  p.Z = Z; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.kp = pl->kp; p.C = C; p.cp = cp; p.PB = PB; p.m0 = pl->m0;
   p.nblk = ceil_div(JP, 32) < 8 ? ceil_div(JP, 32) : 8;
   p.N = 32 * p.nblk;
   p.idesc = make_idesc(p.N, 1, 1, 0);
@@ -653,6 +654,7 @@ static int fill_mix(const Plan* pl, int op, int B, int G, int Ci, int Co, MixPar
   B200_REQUIRE(B >= 1 && 32 % B == 0, "tcgen05 mix: batch %d must divide 32 (use precision fp32 otherwise)", B);
   B200_REQUIRE(G == 1 || ((Ci / G) % 4 == 0 && (Co / G) % 4 == 0), "tcgen05 mix: group slices (%d, %d channels) must be 16-byte aligned", Ci / G, Co / G);
   memset(p, 0, sizeof(*p));
+  p->dense = pl->dense;
   p->L = pl->lmax; p->M = pl->mmax; p->B = B; p->G = G; p->Cig = Ci / G; p->Cog = Co / G;
   p->cpi = round_up(Ci, 4); p->cpo = round_up(Co, 4); p->cop = round_up(Co / G, 4);
   p->shared_w = (op == B200SHT_OP_SHARED);
@@ -729,14 +731,14 @@ int mix_wgrad_umma(const Plan* pl, int op, const float* x, const float* gy, floa
   return launch<MixWgradTraits>(p, grid, st);
 }
 
-int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, cudaStream_t st);  // mix.cu
+int mix_cbias_grad(const float* gy, void* gcb, int L, int M, int B, int Co, int dense, cudaStream_t st);  // mix.cu
 
 int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
                       int Ci, int Co, cudaStream_t st) {
   int rc = 0;
   if (gx) rc = mix_dgrad_umma(pl, op, w, gy, gx, B, G, Ci, Co, st);
   if (!rc && gw) rc = mix_wgrad_umma(pl, op, x, gy, static_cast<float*>(gw), B, G, Ci, Co, st);
-  if (!rc && gcbias) rc = mix_cbias_grad(gy, gcbias, pl->lmax, pl->mmax, B, Co, st);
+  if (!rc && gcbias) rc = mix_cbias_grad(gy, gcbias, pl->lmax, pl->mmax, B, Co, pl->dense, st);
   return rc;
 }
 

@@ -66,11 +66,32 @@ class Plan:
             rc = lib.b200sht_plan_create(ctypes.byref(handle), nlat, nlon, lmax, mmax, cost.ctypes.data_as(_VP), w.ctypes.data_as(_VP),
                                          1 if csphase else 0, _stream(device))
         _lib.check(rc, "b200sht_plan_create")
+        self._finish(handle, device, nlat, nlon, lmax, mmax, 0)
+
+    def _finish(self, handle, device, nlat, nlon, lmax, mmax, m_offset):
+        lib = _lib.load()
         self.handle = handle
         self.device = device
-        self.nlat, self.nlon, self.lmax, self.mmax = nlat, nlon, lmax, mmax
+        self.nlat, self.nlon, self.lmax, self.mmax, self.m_offset = nlat, nlon, lmax, mmax, m_offset
         self.kp = int(lib.b200sht_plan_query(handle, 4))
         self.umma_ok = bool(lib.b200sht_plan_query(handle, 6))
+
+    @classmethod
+    def create_ex(cls, nlat, nlon, lmax, mmax, m_offset, flags, cost, quad_w, csphase, device):
+        """Sub-plans of the distributed SHT (b200sht_plan_create_ex): order offset and/or FFT-only (flags & 1)."""
+        if device.type != "cuda":
+            raise B200ShtError("makani_b200 transforms run on CUDA devices only (no CPU fallback)")
+        lib = _lib.load()
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        quad_w = np.ascontiguousarray(quad_w, dtype=np.float64)
+        handle = _VP()
+        with torch.cuda.device(device):
+            rc = lib.b200sht_plan_create_ex(ctypes.byref(handle), nlat, nlon, lmax, mmax, m_offset, flags, cost.ctypes.data_as(_VP),
+                                            quad_w.ctypes.data_as(_VP), 1 if csphase else 0, _stream(device))
+        _lib.check(rc, "b200sht_plan_create_ex")
+        self = cls.__new__(cls)
+        self._finish(handle, device, nlat, nlon, lmax, mmax, m_offset)
+        return self
 
     def latspec_elems(self, B, C):
         return int(_lib.load().b200sht_latspec_elems(self.handle, B, C))
@@ -221,6 +242,45 @@ class _SpecPack(torch.autograd.Function):
         out = torch.empty((B, C, L, M), dtype=torch.complex64, device=gspec.device)
         _lib.call("b200sht_spec_unpack", L, M, _ptr(gspec.contiguous()), _ptr(out), B, C, _stream(gspec.device))
         return out
+
+
+class _SpecUnpackEx(torch.autograd.Function):
+    """packed spec -> complex64 (B, C, L, M) with an order offset and/or dense storage (distributed path)."""
+
+    @staticmethod
+    def forward(ctx, spec, L, M, B, C, m_offset, dense):
+        out = torch.empty((B, C, L, M), dtype=torch.complex64, device=spec.device)
+        _lib.call("b200sht_spec_unpack_ex", L, M, m_offset, dense, _ptr(spec.contiguous()), _ptr(out), B, C, _stream(spec.device))
+        ctx.dims = (L, M, B, C, m_offset, dense)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L, M, B, C, m_offset, dense = ctx.dims
+        g = g.contiguous()
+        spec = torch.empty(int(_lib.load().b200sht_spec_elems_lm(L, M, B, C)), dtype=torch.float32, device=g.device)
+        _lib.call("b200sht_spec_pack_ex", L, M, m_offset, dense, _ptr(g), _ptr(spec), B, C, _stream(g.device))
+        return spec, None, None, None, None, None, None
+
+
+class _SpecPackEx(torch.autograd.Function):
+    """complex64 (B, C, L, M) -> packed spec with an order offset and/or dense storage."""
+
+    @staticmethod
+    def forward(ctx, coeffs, m_offset, dense):
+        B, C, L, M = coeffs.shape
+        coeffs = coeffs.contiguous()
+        spec = torch.empty(int(_lib.load().b200sht_spec_elems_lm(L, M, B, C)), dtype=torch.float32, device=coeffs.device)
+        _lib.call("b200sht_spec_pack_ex", L, M, m_offset, dense, _ptr(coeffs), _ptr(spec), B, C, _stream(coeffs.device))
+        ctx.dims = (L, M, B, C, m_offset, dense)
+        return spec
+
+    @staticmethod
+    def backward(ctx, gspec):
+        L, M, B, C, m_offset, dense = ctx.dims
+        out = torch.empty((B, C, L, M), dtype=torch.complex64, device=gspec.device)
+        _lib.call("b200sht_spec_unpack_ex", L, M, m_offset, dense, _ptr(gspec.contiguous()), _ptr(out), B, C, _stream(gspec.device))
+        return out, None, None
 
 
 def _as_bc(x, nd_tail=2):

@@ -61,8 +61,9 @@ class _MixPacked(torch.autograd.Function):
         spec = spec.contiguous()
         if weight.dtype != torch.complex64:
             raise B200ShtError(f"spectral weights must be complex64, got {weight.dtype}")
-        if op in _DENSE_OPS:
-            wdev = (cache if cache is not None else PackedWeightCache()).get(weight, op, L, M, G, Ci, Co, precision)
+        base_op = op & 0xFF  # op may carry _lib.DENSE_FLAG (l/m-sharded spectra of the distributed path)
+        if base_op in _DENSE_OPS:
+            wdev = (cache if cache is not None else PackedWeightCache()).get(weight, base_op, L, M, G, Ci, Co, precision)
         else:
             wdev = weight.detach().contiguous()
         y = torch.empty(int(_lib.load().b200sht_spec_elems_lm(L, M, B, Co)), dtype=torch.float32, device=dev)
@@ -82,9 +83,10 @@ class _MixPacked(torch.autograd.Function):
         need_x, need_w, need_cb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and cbshape is not None
         gx = torch.empty(int(lib.b200sht_spec_elems_lm(L, M, B, Ci)), dtype=torch.float32, device=dev) if need_x else None
         gw_dev = None
+        base_op = op & 0xFF
         if need_w:
-            if op in _DENSE_OPS:
-                gw_dev = torch.empty(int(lib.b200sht_mix_weight_elems(op, L, M, G, Ci, Co)), dtype=torch.float32, device=dev)
+            if base_op in _DENSE_OPS:
+                gw_dev = torch.empty(int(lib.b200sht_mix_weight_elems(base_op, L, M, G, Ci, Co)), dtype=torch.float32, device=dev)
             else:
                 gw_dev = torch.empty(wshape, dtype=torch.complex64, device=dev)
         gcb = torch.empty(Co, dtype=torch.complex64, device=dev) if need_cb else None
@@ -92,9 +94,9 @@ class _MixPacked(torch.autograd.Function):
                   _stream(dev))
         gw = None
         if need_w:
-            if op in _DENSE_OPS:
+            if base_op in _DENSE_OPS:
                 gw = torch.empty(wshape, dtype=torch.complex64, device=dev)
-                _lib.call("b200sht_mix_weight_unpack", op, _ptr(gw_dev), _ptr(gw), L, G, Ci, Co, _stream(dev))
+                _lib.call("b200sht_mix_weight_unpack", base_op, _ptr(gw_dev), _ptr(gw), L, G, Ci, Co, _stream(dev))
             else:
                 gw = gw_dev
         if gcb is not None:
@@ -184,6 +186,8 @@ class SpectralConv(nn.Module):
             self.bias.sharded_dims_mp = [None, None, None, None]
 
         self._op = _op_code(operator_type, separable)
+        if getattr(self.inverse_transform, "packed_dense", False):
+            self._op |= _lib.DENSE_FLAG
         self._wcache = PackedWeightCache()
 
     def forward(self, x):
