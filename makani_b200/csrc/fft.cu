@@ -263,17 +263,24 @@ __device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m
 }
 
 // =========================================================================================== compile-time plans
+// Real rows of even length N are transformed through ONE complex FFT of length H = N/2 each (z[n] = x[2n] + i x[2n+1], loaded
+// as one 4- or 8-byte word), followed by the split  X[m] = E[m] + W_N^m O[m],  E = (Z[m] + conj Z[H-m])/2,
+// O = (Z[m] - conj Z[H-m])/(2i).  A CTA owns ROWS = 8 consecutive latitude rows; the threads form GROUPS groups of TPG threads,
+// a group owns RPT = ROWS/GROUPS rows and one thread owns a butterfly index of those rows (twiddles and skewed indices are
+// computed once per index).
 template <int R0>
 __host__ __device__ constexpr int skew(int i) { return i + i / R0; }
 
-// stage s of a compile-time plan: smem (skewed) -> smem (skewed).  One thread owns butterfly index j of ALL pairs: the
-// R-1 twiddles and the 2R skewed indices are computed once and reused for the PAIRS independent transforms.
-template <int N, int R, int Ns, int R0, int THREADS, int PAIRS>
-__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int bufstride) {
-  constexpr int NB = N / R;
-  for (int j = threadIdx.x; j < NB; j += THREADS) {
+template <int H, int R0>
+__host__ __device__ constexpr int ct_bufstride() { return (skew<R0>(H) + 2) | 1; }  // odd stride: rows land on different banks
+
+// stage of a compile-time plan: smem (skewed) -> smem (skewed), rows row0 .. row0 + RPT - 1
+template <int H, int R, int Ns, int R0, int TPG, int RPT>
+__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int bufstride, int t, int row0) {
+  constexpr int NB = H / R;
+  for (int j = t; j < NB; j += TPG) {
     const int k = j % Ns;
-    const int tstep = k * (N / (Ns * R));
+    const int tstep = k * (H / (Ns * R));
     const int j0 = (j - k) * R + k;
     float2 w[R];
     int si[R], di[R];
@@ -283,10 +290,10 @@ __device__ __forceinline__ void ct_stage(const float2* in, float2* out, const fl
       di[r] = skew<R0>(j0 + r * Ns);
       if (Ns > 1 && r > 0) w[r] = tw[r * tstep];
     }
-#pragma unroll 2
-    for (int q = 0; q < PAIRS; ++q) {
-      const float2* src = in + q * bufstride;
-      float2* dst = out + q * bufstride;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const float2* src = in + (row0 + q) * bufstride;
+      float2* dst = out + (row0 + q) * bufstride;
       float2 v[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -294,77 +301,209 @@ __device__ __forceinline__ void ct_stage(const float2* in, float2* out, const fl
         if (Ns > 1 && r > 0) a = cmul(a, w[r]);
         v[r] = a;
       }
-      Butterfly<R>::run(v, tw, N);
+      Butterfly<R>::run(v, tw, H);
 #pragma unroll
       for (int r = 0; r < R; ++r) dst[di[r]] = v[r];
     }
   }
 }
 
-template <int N, int R0>
-__host__ __device__ constexpr int ct_bufstride() { return (skew<R0>(N) + 2) | 1; }  // odd stride: the 4 pairs land on different banks
+__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* p) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+  return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
+}
+__device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st_pair(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
 
-// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2), R2 == 1 for two stages
-template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
-__global__ void __launch_bounds__(THREADS) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
-  constexpr int N = R0 * R1 * R2;
-  constexpr int BS = ct_bufstride<N, R0>();
-  constexpr int KC = 2 * PAIRS;
+// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2) for H = nlon / 2, R2 == 1 for two stages
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
+__global__ void __launch_bounds__(GROUPS * TPG) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
+  constexpr int H = R0 * R1 * R2, N = 2 * H;
+  constexpr int BS = ct_bufstride<H, R0>();
+  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
+  static_assert(ROWS % GROUPS == 0 && ROWS % 4 == 0, "row grouping");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tw = reinterpret_cast<float2*>(smem_raw);
-  float2* b0 = tw + N;
-  float2* b1 = b0 + PAIRS * BS;
-  const int k0 = blockIdx.x * KC;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);   // W_H^t = W_N^(2t)
+  float2* b0 = tw + H;
+  float2* b1 = b0 + ROWS * BS;
+  const int k0 = blockIdx.x * ROWS;
   const int r = blockIdx.y;
-  for (int t = threadIdx.x; t < N; t += THREADS) tw[t] = prm.twiddle[t];
+  const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
+  const int row0 = grp * RPT;
+  for (int i = threadIdx.x; i < H; i += THREADS) tw[i] = prm.twiddle[2 * i];
 
-  // ---- stage 0 fused with the global load: thread j of pair q reads elements j + r * N/R0 of rows k0+2q, k0+2q+1
+  // ---- stage 0 fused with the global load
   {
-    constexpr int NB = N / R0;
+    constexpr int NB = H / R0;
     const T* base = x + ((size_t)r * prm.nlat + k0) * N;
-    for (int j = threadIdx.x; j < NB; j += THREADS) {
+    for (int j = t; j < NB; j += TPG) {
       int di[R0];
 #pragma unroll
       for (int rr = 0; rr < R0; ++rr) di[rr] = skew<R0>(j * R0 + rr);
-#pragma unroll 2
-      for (int q = 0; q < PAIRS; ++q) {
-        const bool va = (k0 + 2 * q) < prm.nlat, vb = (k0 + 2 * q + 1) < prm.nlat;
-        const T* ra = base + (size_t)(2 * q) * N + j;
-        const T* rb = ra + N;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = row0 + q;
+        const bool valid = (k0 + row) < prm.nlat;
+        const T* rp = base + (size_t)row * N + 2 * j;
         float2 v[R0];
 #pragma unroll
-        for (int rr = 0; rr < R0; ++rr) v[rr] = make_float2(va ? ld_as_float(ra + rr * NB) : 0.f, vb ? ld_as_float(rb + rr * NB) : 0.f);
-        Butterfly<R0>::run(v, nullptr, N);
-        float2* dst = b0 + q * BS;
+        for (int rr = 0; rr < R0; ++rr) v[rr] = valid ? ld_pair(rp + 2 * rr * NB) : make_float2(0.f, 0.f);
+        Butterfly<R0>::run(v, nullptr, H);
+        float2* dst = b0 + row * BS;
 #pragma unroll
         for (int rr = 0; rr < R0; ++rr) dst[di[rr]] = v[rr];
       }
     }
   }
   __syncthreads();
-  ct_stage<N, R1, R0, R0, THREADS, PAIRS>(b0, b1, tw, BS);
+  ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw, BS, t, row0);
   __syncthreads();
-  float2* res = b1;
+  const float2* res = b1;
   if (R2 > 1) {
-    ct_stage<N, (R2 > 1 ? R2 : 2), R0 * R1, R0, THREADS, PAIRS>(b1, b0, tw, BS);
+    ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw, BS, t, row0);
     __syncthreads();
     res = b0;
   }
 
-  // ---- split, truncate, scale, store: item = (m, p, kk), kk fastest -> 32-byte sectors
-  const int total = prm.mmax * 2 * KC;
-  for (int e = threadIdx.x; e < total; e += THREADS) {
-    const int kk = e % KC;
-    const int mp = e / KC;
-    const int p = mp & 1, m = mp >> 1;
-    const int q = kk >> 1;
-    const float2 Z = res[q * BS + skew<R0>(m)];
-    const float2 Zm = res[q * BS + skew<R0>(m == 0 ? 0 : N - m)];
-    float2 A, Bq;
-    split_pair(Z, Zm, A, Bq);
-    const float2 val = (kk & 1) ? Bq : A;
-    const int k = k0 + kk;
-    if (k < prm.kp) X[(((size_t)m * 2 + p) * prm.R + r) * prm.kp + k] = finish_analysis(prm, (p ? val.y : val.x) * mode_scale_analysis(prm, m, k));
+  // ---- split + truncate + scale + store: item = (m, quad of 4 rows); two 16-byte stores (re, im) per item
+  constexpr int QUADS = ROWS / 4;
+  for (int e = threadIdx.x; e < prm.mmax * QUADS; e += THREADS) {
+    const int qd = e % QUADS, m = e / QUADS;
+    const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
+    const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
+    float re[4], imv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = qd * 4 + i;
+      const float2 Z = res[row * BS + im], Zc = res[row * BS + ic];
+      const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
+      const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
+      const float2 WO = cmul(wm, Od);
+      const float sc = mode_scale_analysis(prm, m, k0 + row);
+      re[i] = finish_analysis(prm, (E.x + WO.x) * sc);
+      imv[i] = finish_analysis(prm, (E.y + WO.y) * sc);
+    }
+    const int k = k0 + qd * 4;
+    if (k < prm.kp) {
+      float* dst = X + (((size_t)m * 2) * prm.R + r) * prm.kp + k;
+      *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
+      *reinterpret_cast<float4*>(dst + (size_t)prm.R * prm.kp) = make_float4(imv[0], imv[1], imv[2], imv[3]);
+    }
+  }
+}
+
+// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
+__global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
+  constexpr int H = R0 * R1 * R2, N = 2 * H;
+  constexpr int BS = ct_bufstride<H, R0>();
+  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
+  constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
+  constexpr int NsL = H / RL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* b0 = tw + H;
+  float2* b1 = b0 + ROWS * BS;
+  const int k0 = blockIdx.x * ROWS;
+  const int r = blockIdx.y;
+  const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
+  const int row0 = grp * RPT;
+  const int mmax = prm.mmax;
+  for (int i = threadIdx.x; i < H; i += THREADS) tw[i] = prm.twiddle[2 * i];
+
+  // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re).
+  // item = (q in [0, H/2], quad of 4 rows): reads X[q] and X[H-q] once, writes Z'[q] and Z'[H-q].
+  constexpr int QUADS = ROWS / 4;
+  for (int e = threadIdx.x; e < (H / 2 + 1) * QUADS; e += THREADS) {
+    const int qd = e % QUADS, q = e / QUADS;
+    const int q2 = H - q;                                    // partner index (q2 == H for q == 0)
+    const int k = k0 + qd * 4;
+    float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f}, br[4] = {0.f, 0.f, 0.f, 0.f}, bi[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < prm.kp) {
+      if (q < mmax) {
+        const float* src = Zs + (((size_t)q * 2) * prm.R + r) * prm.kp + k;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp);
+        ar[0] = a.x; ar[1] = a.y; ar[2] = a.z; ar[3] = a.w; ai[0] = b.x; ai[1] = b.y; ai[2] = b.z; ai[3] = b.w;
+      }
+      if (q2 < mmax) {
+        const float* src = Zs + (((size_t)q2 * 2) * prm.R + r) * prm.kp + k;
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp);
+        br[0] = a.x; br[1] = a.y; br[2] = a.z; br[3] = a.w; bi[0] = b.x; bi[1] = b.y; bi[2] = b.z; bi[3] = b.w;
+      }
+    }
+    const bool a_self = (q == 0), b_self = (q2 == H);        // DC and Nyquist: imaginary part ignored, no halving
+    const float ha = (prm.scale_mode == 1 && !a_self) ? 0.5f : 1.f;
+    const float hb = (prm.scale_mode == 1 && !b_self) ? 0.5f : 1.f;
+    const float2 wq = __ldg(prm.twiddle + q);                 // W_N^q ; W_N^-q = conj
+    const float2 wq2 = (q2 < N) ? __ldg(prm.twiddle + (q2 % N)) : make_float2(1.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = qd * 4 + i;
+      const bool valid = (k + i) < prm.nlat;
+      float Ar = valid ? ar[i] * ha : 0.f, Ai = (valid && !a_self) ? ai[i] * ha : 0.f;   // A = X[q]
+      float Br = valid ? br[i] * hb : 0.f, Bi = (valid && !b_self) ? bi[i] * hb : 0.f;   // B = X[H-q]
+      // Z'[q] = (A + conj B) + i (A - conj B) conj(wq)
+      {
+        const float sr = Ar + Br, si2 = Ai - Bi;              // A + conj B
+        const float dr = Ar - Br, dii = Ai + Bi;              // A - conj B
+        const float tr = dr * wq.x + dii * wq.y, ti = dii * wq.x - dr * wq.y;   // (A - conj B) * conj(wq)
+        const float zr = sr - ti, zi = si2 + tr;              // + i * t
+        b0[row * BS + skew<R0>(q)] = make_float2(zi, zr);
+      }
+      if (q != 0 && q2 != q) {
+        // Z'[q2] = (B + conj A) + i (B - conj A) conj(wq2)
+        const float sr = Br + Ar, si2 = Bi - Ai;
+        const float dr = Br - Ar, dii = Bi + Ai;
+        const float tr = dr * wq2.x + dii * wq2.y, ti = dii * wq2.x - dr * wq2.y;
+        const float zr = sr - ti, zi = si2 + tr;
+        b0[row * BS + skew<R0>(q2)] = make_float2(zi, zr);
+      }
+    }
+  }
+  __syncthreads();
+  ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, tw, BS, t, row0);
+  __syncthreads();
+  const float2* src = b1;
+  if (R2 > 1) {
+    ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw, BS, t, row0);
+    __syncthreads();
+    src = b0;
+  }
+  // ---- last stage fused with the store: butterfly j yields z[e], e = j + rr * NsL, and (x[2e], x[2e+1]) = (Im, Re) of the swapped result
+  {
+    T* base = y + ((size_t)r * prm.nlat + k0) * N;
+    const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
+    for (int j = t; j < NsL; j += TPG) {
+      float2 w[RL];
+      int si[RL];
+#pragma unroll
+      for (int rr = 0; rr < RL; ++rr) {
+        si[rr] = skew<R0>(j + rr * NsL);
+        if (rr > 0) w[rr] = tw[rr * j];   // k = j, H / (Ns * R) = 1
+      }
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int row = row0 + q;
+        const float2* s = src + row * BS;
+        float2 v[RL];
+#pragma unroll
+        for (int rr = 0; rr < RL; ++rr) {
+          float2 a = s[si[rr]];
+          if (rr > 0) a = cmul(a, w[rr]);
+          v[rr] = a;
+        }
+        Butterfly<RL>::run(v, tw, H);
+        if (k0 + row < prm.nlat) {
+          const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + row] : 1.f;
+          T* rp = base + (size_t)row * N + 2 * j;
+#pragma unroll
+          for (int rr = 0; rr < RL; ++rr) st_pair(rp + 2 * rr * NsL, v[rr].y * sc + bias, v[rr].x * sc + bias);
+        }
+      }
+    }
   }
 }
 
@@ -399,71 +538,6 @@ __device__ __forceinline__ void fill_spectrum(const float* __restrict__ Zs, floa
     // V[m] = (ar - bi) + i (ai + br);  V[N-m] = (ar + bi) + i (br - ai)   -- stored swapped (y, x)
     b0[q * bufstride + idx(m)] = make_float2(ai + br, ar - bi);
     if (!self_conj) b0[q * bufstride + idx(N - m)] = make_float2(br - ai, ar + bi);
-  }
-}
-
-// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]
-template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
-__global__ void __launch_bounds__(THREADS) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
-  constexpr int N = R0 * R1 * R2;
-  constexpr int BS = ct_bufstride<N, R0>();
-  constexpr int KC = 2 * PAIRS;
-  constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
-  constexpr int NsL = N / RL;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tw = reinterpret_cast<float2*>(smem_raw);
-  float2* b0 = tw + N;
-  float2* b1 = b0 + PAIRS * BS;
-  const int k0 = blockIdx.x * KC;
-  const int r = blockIdx.y;
-  for (int t = threadIdx.x; t < N; t += THREADS) tw[t] = prm.twiddle[t];
-  fill_spectrum(Zs, b0, BS, PAIRS, THREADS, prm, k0, r, [](int i) { return skew<R0>(i); });
-  __syncthreads();
-  // stage 0: b0 -> b1
-  ct_stage<N, R0, 1, R0, THREADS, PAIRS>(b0, b1, tw, BS);
-  __syncthreads();
-  const float2* src = b1;
-  if (R2 > 1) {
-    ct_stage<N, R1, R0, R0, THREADS, PAIRS>(b1, b0, tw, BS);
-    __syncthreads();
-    src = b0;
-  }
-  // last stage fused with the store: butterfly j produces natural-order outputs j + rr * NsL;  a[e] = v.y, b[e] = v.x
-  {
-    T* base = y + ((size_t)r * prm.nlat + k0) * N;
-    const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
-    for (int j = threadIdx.x; j < NsL; j += THREADS) {
-      float2 w[RL];
-      int si[RL];
-#pragma unroll
-      for (int rr = 0; rr < RL; ++rr) {
-        si[rr] = skew<R0>(j + rr * NsL);
-        if (rr > 0) w[rr] = tw[rr * j];   // k = j, N / (Ns * R) = 1
-      }
-#pragma unroll 2
-      for (int q = 0; q < PAIRS; ++q) {
-        const float2* s = src + q * BS;
-        float2 v[RL];
-#pragma unroll
-        for (int rr = 0; rr < RL; ++rr) {
-          float2 a = s[si[rr]];
-          if (rr > 0) a = cmul(a, w[rr]);
-          v[rr] = a;
-        }
-        Butterfly<RL>::run(v, tw, N);
-        const int ka = k0 + 2 * q;
-        const bool va = ka < prm.nlat, vb = ka + 1 < prm.nlat;
-        const float sa = (prm.scale_mode == 1 && va) ? prm.rowscale[ka] : 1.f;
-        const float sb = (prm.scale_mode == 1 && vb) ? prm.rowscale[ka + 1] : 1.f;
-        T* ra = base + (size_t)(2 * q) * N + j;
-        T* rb = ra + N;
-#pragma unroll
-        for (int rr = 0; rr < RL; ++rr) {
-          if (va) st_from_float(ra + rr * NsL, v[rr].y * sa + bias);
-          if (vb) st_from_float(rb + rr * NsL, v[rr].x * sb + bias);
-        }
-      }
-    }
   }
 }
 
@@ -582,47 +656,50 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
   return prm;
 }
 
-template <typename T, int PAIRS, int THREADS, int R0, int R1, int R2>
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
 static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
-  constexpr int N = R0 * R1 * R2;
-  constexpr size_t smem = sizeof(float2) * ((size_t)N + 2 * PAIRS * ct_bufstride<N, R0>());
+  constexpr int H = R0 * R1 * R2;
+  constexpr size_t smem = sizeof(float2) * ((size_t)H + 2 * ROWS * ct_bufstride<H, R0>());
   static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
-  dim3 grid(ceil_div(pl->kp, 2 * PAIRS), prm.R);
+  dim3 grid(ceil_div(pl->kp, ROWS), prm.R);
   if (dir == 0) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_analysis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2><<<grid, THREADS, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
   } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_synthesis_ct_kernel<T, PAIRS, THREADS, R0, R1, R2><<<grid, THREADS, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
   }
   B200_CHECK_LAUNCH();
   return 0;
 }
 
-// lengths with a compile-time plan: (PAIRS, THREADS, R0, R1, R2), N = R0*R1*R2.  R0 is a power of two where possible (the
-// skew i + i/R0 becomes a shift); THREADS ~ max_s N/R_s because one thread owns a butterfly index of all PAIRS transforms.
-#define CT_PLANS(X)        \
-  X(4, 160, 16, 10, 9)     /* 1440 */ \
-  X(4, 96, 8, 10, 9)       /*  720 */ \
-  X(4, 96, 8, 10, 6)       /*  480 */ \
-  X(4, 96, 8, 9, 5)        /*  360 */ \
-  X(4, 64, 8, 6, 5)        /*  240 */ \
-  X(4, 64, 4, 9, 5)        /*  180 */ \
-  X(4, 64, 8, 6, 3)        /*  144 */ \
-  X(8, 32, 8, 4, 4)        /*  128 */ \
-  X(8, 32, 8, 4, 3)        /*   96 */ \
-  X(8, 32, 8, 3, 3)        /*   72 */ \
-  X(8, 32, 4, 4, 4)        /*   64 */ \
-  X(8, 64, 16, 4, 4)       /*  256 */ \
-  X(4, 64, 8, 8, 8)        /*  512 */ \
-  X(4, 128, 16, 8, 8)      /* 1024 */ \
-  X(2, 256, 16, 15, 12)    /* 2880 */
+// lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
+// i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
+#define CT_PLANS(X)          \
+  X(8, 4, 96, 8, 10, 9)      /* nlon 1440 */ \
+  X(8, 4, 96, 8, 9, 5)       /* nlon  720 */ \
+  X(8, 4, 64, 8, 6, 5)       /* nlon  480 */ \
+  X(8, 4, 64, 4, 9, 5)       /* nlon  360 */ \
+  X(8, 4, 64, 8, 5, 3)       /* nlon  240 */ \
+  X(8, 4, 64, 2, 9, 5)       /* nlon  180 */ \
+  X(8, 4, 32, 8, 3, 3)       /* nlon  144 */ \
+  X(8, 8, 32, 4, 4, 4)       /* nlon  128 */ \
+  X(8, 8, 32, 4, 4, 3)       /* nlon   96 */ \
+  X(8, 8, 32, 4, 3, 3)       /* nlon   72 */ \
+  X(8, 8, 32, 4, 8, 1)       /* nlon   64 */ \
+  X(8, 4, 32, 8, 4, 4)       /* nlon  256 */ \
+  X(8, 4, 64, 8, 8, 4)       /* nlon  512 */ \
+  X(8, 4, 64, 8, 8, 8)       /* nlon 1024 */ \
+  X(8, 2, 160, 16, 10, 9)    /* nlon 2880 */
 
 template <typename T>
 static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st, bool* handled) {
+  *handled = false;
+  // the compile-time plans move element pairs / quads with vector loads: both tensors must be 16-byte aligned
+  if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return 0;
   *handled = true;
-#define X(P, TH, A, B_, C_) \
-  if (pl->nlon == (A) * (B_) * (C_)) return launch_ct<T, P, TH, A, B_, C_>(pl, dir, in, out, prm, st);
+#define X(RW, G, TP, A, B_, C_) \
+  if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_>(pl, dir, in, out, prm, st);
   CT_PLANS(X)
 #undef X
   *handled = false;

@@ -288,16 +288,22 @@ struct SynTraits {
     const int k = t.k0 + warp * 32 + lane;
     const int JP = p.PB * p.cp;
     float v[32];
+    // column jp = pb * cp + c -> row (m, pb, c) of Z; (pb, c) and the row pointer are advanced incrementally (no division per element)
+    int pb = t.n0 / p.cp, c = t.n0 - pb * p.cp;
+    float* ptr = p.Z + (((size_t)t.m * p.PB + pb) * p.C + c) * p.kp + (k < p.kp ? k : 0);
     for (int n0 = 0; n0 < p.N; n0 += 32) {
       if (t.n0 + n0 >= JP) break;
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, v);
-      if (k >= p.kp) continue;
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const int jp = t.n0 + n0 + q;
-        if (jp >= JP) break;
-        const int pb = jp / p.cp, c = jp - pb * p.cp;
-        if (c < p.C) p.Z[(((size_t)t.m * p.PB + pb) * p.C + c) * p.kp + k] = (nk > 0) ? v[q] : 0.f;
+        if (pb < p.PB && c < p.C && k < p.kp) *ptr = (nk > 0) ? v[q] : 0.f;
+        ++c;
+        ptr += p.kp;
+        if (c == p.cp) {  // next (re/im, batch) plane: skip the channel padding
+          c = 0;
+          ++pb;
+          ptr -= (size_t)(p.cp - p.C) * p.kp;
+        }
       }
     }
   }
