@@ -1,9 +1,10 @@
 // tcgen05 / TMA path (B200SHT_PREC_TF32): the Legendre contractions and the dense channel mix as TMA-fed tensor-core
 // GEMMs with fp32 accumulators in TMEM.
 //
-//   one engine (umma_kernel<Traits>): 4 warps; warp 0 lane 0 = TMA producer, warp 1 lane 0 = tcgen05.mma issuer, all four
-//   warps = epilogue (warp w owns TMEM lanes 32w..32w+31).  smem ring of `stages` operand stages guarded by full/empty
-//   mbarriers; tcgen05.commit releases a stage and finally signals the epilogue.
+//   one persistent engine (umma_kernel<Traits>, one CTA per SM walking the tile list): warp 0 lane 0 = TMA producer, warp 1
+//   lane 0 = tcgen05.mma issuer, warps 2..5 = epilogue (warp w owns TMEM lanes 32(w%4)..+31).  A ring of `stages` operand
+//   stages guarded by full/empty mbarriers runs continuously across tiles; two accumulator sets in TMEM (acc_full/acc_empty)
+//   let the epilogue of tile i overlap the main loop of tile i+1.
 //
 //   five Traits supply the per-operation pieces (tile coordinates, TMA boxes, MMA issue list, epilogue):
 //     AnaTraits   spec[l][m][n]  = sum_k P[m][l][k] X[m][n][k]          A K-major,  B K-major     (RealSHT einsum "...km,mlk->...lm")
@@ -136,15 +137,26 @@ __host__ __device__ constexpr uint32_t make_idesc(int N, int a_mn_major, int b_m
 }
 
 // ======================================================================================================= engine
-constexpr int kUmmaThreads = 128;
+constexpr int kUmmaThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
 constexpr int kMaxStages = 8;
 
+struct EngineParams {
+  int stages;
+  uint32_t stage_bytes, tx_bytes, tmem_cols;
+  int gx, gy, gz;          // logical tile grid (x fastest); CTAs walk it round-robin
+  int acc_cols, nbuf;      // TMEM columns of one accumulator set, number of sets (2: epilogue of tile i overlaps main loop of i+1)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent engine: one CTA per SM loops over tiles.  The operand ring (full/empty) runs continuously across tiles, so the
+// TMA producer prefetches the next tile while the tensor core finishes the current one and the four epilogue warps drain the
+// previous accumulator set (acc_full / acc_empty).
 template <class T>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_constant__ typename T::Params p) {
   extern __shared__ uint8_t smem_raw[];
-  typename T::Tile tile;
-  if (!T::make_tile(p, tile)) return;  // uniform per CTA
-
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
@@ -152,13 +164,14 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
   const uint32_t stage_bytes = p.stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(gbase + (size_t)stages * stage_bytes);
   uint64_t* empty = full + kMaxStages;
-  uint64_t* accum = empty + kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  uint64_t* acc_full = empty + kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
     T::prefetch(p);
   }
@@ -167,43 +180,70 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int nk = T::num_kblocks(p, tile);
+  const int ntiles = p.gx * p.gy * p.gz;
+  const int nbuf = p.nbuf;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % stages, it = kb / stages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-        mbar_expect_tx(&full[s], p.tx_bytes);
-        T::load(p, tile, kb, base + s * stage_bytes, &full[s]);
+      int kbg = 0;   // k-block counter across tiles: position in the operand ring
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        typename T::Tile tile;
+        if (!T::make_tile(p, tile, ti % p.gx, (ti / p.gx) % p.gy, ti / (p.gx * p.gy))) continue;
+        const int nk = T::num_kblocks(p, tile);
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % stages, it = kbg / stages;
+          if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+          mbar_expect_tx(&full[s], p.tx_bytes);
+          T::load(p, tile, kb, base + s * stage_bytes, &full[s]);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % stages, it = kb / stages;
-        mbar_wait(&full[s], it & 1);
-        tc_fence_after();
-        T::mma(p, tile, base + s * stage_bytes, tmem, kb > 0);
-        umma_commit(&empty[s]);
+      int kbg = 0, i = 0;
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        typename T::Tile tile;
+        if (!T::make_tile(p, tile, ti % p.gx, (ti / p.gx) % p.gy, ti / (p.gx * p.gy))) continue;
+        const int nk = T::num_kblocks(p, tile);
+        const int buf = i % nbuf, use = i / nbuf;
+        if (use > 0) {  // the epilogue must have drained this accumulator set
+          mbar_wait(&acc_empty[buf], (use - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const int s = kbg % stages, it = kbg / stages;
+          mbar_wait(&full[s], it & 1);
+          tc_fence_after();
+          T::mma(p, tile, base + s * stage_bytes, tmem + buf * p.acc_cols, kb > 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+        ++i;
       }
-      umma_commit(accum);
     }
     __syncwarp();
+  } else {
+    const int quad = warp & 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
+    int i = 0;
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+      typename T::Tile tile;
+      if (!T::make_tile(p, tile, ti % p.gx, (ti / p.gx) % p.gy, ti / (p.gx * p.gy))) continue;
+      const int nk = T::num_kblocks(p, tile);
+      const int buf = i % nbuf, use = i / nbuf;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc_fence_after();
+      T::epilogue(p, tile, tmem + buf * p.acc_cols, quad, lane, nk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      ++i;
+    }
   }
-  mbar_wait(accum, 0);
-  tc_fence_after();
-  T::epilogue(p, tile, tmem, warp, lane, nk);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
 }
-
-struct EngineParams {
-  int stages;
-  uint32_t stage_bytes, tx_bytes, tmem_cols;
-};
 
 // ================================================================================================ AnaTraits
 struct AnaTraits {
@@ -215,11 +255,11 @@ struct AnaTraits {
     uint32_t idesc;
   };
   struct Tile { int m, l0, c0, pb0; };
-  __device__ static bool make_tile(const Params& p, Tile& t) {
-    t.m = blockIdx.z;
-    t.l0 = lstart(p.m0 + t.m) + 128 * blockIdx.x;
-    t.c0 = (blockIdx.y % p.n_ct) * p.Cc;
-    t.pb0 = (blockIdx.y / p.n_ct) * p.PBc;
+  __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) {
+    t.m = bz;
+    t.l0 = lstart(p.m0 + t.m) + 128 * bx;
+    t.c0 = (by % p.n_ct) * p.Cc;
+    t.pb0 = (by / p.n_ct) * p.PBc;
     return t.l0 < p.L;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
@@ -264,10 +304,10 @@ struct SynTraits {
     uint32_t idesc;
   };
   struct Tile { int m, k0, n0, lbeg; };
-  __device__ static bool make_tile(const Params& p, Tile& t) {
-    t.m = blockIdx.z;
-    t.k0 = 128 * blockIdx.x;
-    t.n0 = p.N * blockIdx.y;
+  __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) {
+    t.m = bz;
+    t.k0 = 128 * bx;
+    t.n0 = p.N * by;
     t.lbeg = lstart(p.m0 + t.m);
     return true;
   }
@@ -332,11 +372,11 @@ struct MixParams : EngineParams {
 struct MixFwdTraits {
   using Params = MixParams;
   struct Tile { int l, m0, g, o0, lg; };
-  __device__ static bool make_tile(const Params& p, Tile& t) {
-    t.l = blockIdx.z;
-    t.m0 = blockIdx.x * p.Mt;
-    t.g = blockIdx.y / p.n_nt;
-    t.o0 = (blockIdx.y % p.n_nt) * p.N;
+  __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) {
+    t.l = bz;
+    t.m0 = bx * p.Mt;
+    t.g = by / p.n_nt;
+    t.o0 = (by % p.n_nt) * p.N;
     t.lg = (p.shared_w ? 0 : t.l * p.G) + t.g;
     return t.m0 < mend_d(t.l, p.M, p.dense);
   }
@@ -399,7 +439,7 @@ struct MixFwdTraits {
 struct MixDgradTraits {
   using Params = MixParams;   // tmX = gy (channels = Cout), out = gx; N tiles over i
   using Tile = MixFwdTraits::Tile;  // o0 is the first input channel i0 of the tile
-  __device__ static bool make_tile(const Params& p, Tile& t) { return MixFwdTraits::make_tile(p, t); }
+  __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) { return MixFwdTraits::make_tile(p, t, bx, by, bz); }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmW); }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.Cog + 31) / 32; }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
@@ -429,11 +469,11 @@ struct MixDgradTraits {
 struct MixWgradTraits {
   using Params = MixParams;   // tmX = x (A, rows i), tmX2 = gy (B, cols o); K = spectral rows (m, b)
   struct Tile { int lz, i0, g, o0; };
-  __device__ static bool make_tile(const Params& p, Tile& t) {
-    t.lz = blockIdx.z;
-    t.i0 = blockIdx.x * 128;
-    t.g = blockIdx.y / p.n_nt;
-    t.o0 = (blockIdx.y % p.n_nt) * p.N;
+  __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) {
+    t.lz = bz;
+    t.i0 = bx * 128;
+    t.g = by / p.n_nt;
+    t.o0 = (by % p.n_nt) * p.N;
     return true;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmX); prefetch_tmap(&p.tmX2); }
@@ -562,24 +602,41 @@ void umma_plan_destroy(Plan* pl) {
 
 constexpr size_t kSmemMax = 232448 - 2048;  // 227 KB minus barriers / alignment slack
 
-static void pick_stages(EngineParams* e, uint32_t stage_bytes, int max_useful) {
+static void pick_stages(EngineParams* e, uint32_t stage_bytes, int /*k-blocks per tile: the ring runs across tiles*/) {
   e->stage_bytes = stage_bytes;
-  size_t budget = (3ull * stage_bytes <= 110 * 1024) ? 110 * 1024 : kSmemMax;  // two CTAs per SM when three stages fit in half
-  int s = (int)(budget / stage_bytes);
+  int s = (int)(kSmemMax / stage_bytes);   // persistent: one CTA per SM owns the whole shared memory
   if (s > kMaxStages) s = kMaxStages;
-  if (s > max_useful) s = max_useful;
   if (s < 2) s = 2;
   e->stages = s;
 }
-static size_t smem_bytes(const EngineParams& e) { return (size_t)e.stages * e.stage_bytes + 1024 /*align*/ + (2 * kMaxStages + 2) * 8 + 16; }
+static size_t smem_bytes(const EngineParams& e) { return (size_t)e.stages * e.stage_bytes + 1024 /*align*/ + (2 * kMaxStages + 4) * 8 + 16; }
 static uint32_t tmem_cols_pow2(int cols) { uint32_t c = 32; while ((int)c < cols) c <<= 1; return c; }
+// accumulator sets: `cols` TMEM columns per tile; two sets (double buffering) when they fit in the 512 columns
+static void set_accumulators(EngineParams* e, int cols) {
+  e->acc_cols = round_up(cols, 32);
+  e->nbuf = (2 * e->acc_cols <= 512) ? 2 : 1;
+  e->tmem_cols = tmem_cols_pow2(e->acc_cols * e->nbuf);
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
 
 template <class T>
-static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
+static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
+  p.gx = (int)grid.x; p.gy = (int)grid.y; p.gz = (int)grid.z;
+  const long long ntiles = (long long)grid.x * grid.y * grid.z;
+  if (ntiles <= 0) return 0;
   const size_t smem = smem_bytes(p);
   if (smem > 232448) { set_error("umma: %zu bytes of shared memory needed", smem); return B200SHT_ERR_UNSUPPORTED; }
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_kernel<T><<<grid, kUmmaThreads, smem, st>>>(p);
+  const int ctas = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  umma_kernel<T><<<ctas, kUmmaThreads, smem, st>>>(p);
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -610,7 +667,7 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
   const uint32_t bbytes = (uint32_t)round_up(p.N * 128, 1024);
   pick_stages(&p, 16384 + bbytes, ceil_div(pl->nlat, 32));
   p.tx_bytes = 16384 + (uint32_t)rows * 128;
-  p.tmem_cols = tmem_cols_pow2(p.N);
+  set_accumulators(&p, p.N);
   dim3 grid(ceil_div(pl->lmax, 128), p.n_ct * ceil_div(PB, p.PBc), pl->mmax);
   return launch<AnaTraits>(p, grid, st);
 }
@@ -637,7 +694,7 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   }
   pick_stages(&p, 16384 + 4096 * p.nblk, ceil_div(pl->lmax, 32));
   p.tx_bytes = 16384 + 4096 * p.nblk;
-  p.tmem_cols = tmem_cols_pow2(p.N);
+  set_accumulators(&p, p.N);
   dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), pl->mmax);
   return launch<SynTraits>(p, grid, st);
 }
@@ -686,7 +743,7 @@ int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, cons
   if (rc) return rc;
   pick_stages(&p, 32768 + 8192 * p.nblk, ceil_div(p.Cig, 32));
   p.tx_bytes = 2u * (uint32_t)(p.Mt * B) * 128 + 8192u * p.nblk;
-  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  set_accumulators(&p, 2 * p.N);
   dim3 grid(ceil_div(p.M, p.Mt), p.n_nt * G, p.L);
   return launch<MixFwdTraits>(p, grid, st);
 }
@@ -711,7 +768,7 @@ int mix_dgrad_umma(const Plan* pl, int op, const void* w, const float* gy, float
   if (rc) return rc;
   pick_stages(&p, 32768 + 2 * bb, ceil_div(p.Cog, 32));
   p.tx_bytes = 2u * (uint32_t)(p.Mt * B) * 128 + 2u * (uint32_t)p.N * 128;
-  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  set_accumulators(&p, 2 * p.N);
   dim3 grid(ceil_div(p.M, p.Mt), p.n_nt * G, p.L);
   return launch<MixDgradTraits>(p, grid, st);
 }
@@ -732,7 +789,7 @@ int mix_wgrad_umma(const Plan* pl, int op, const float* x, const float* gy, floa
   if (rc) return rc;
   pick_stages(&p, 32768 + 8192 * p.nblk, 8);
   p.tx_bytes = 32768u + 8192u * p.nblk;
-  p.tmem_cols = tmem_cols_pow2(2 * p.N);
+  set_accumulators(&p, 2 * p.N);
   dim3 grid(ceil_div(p.Cig, 128), p.n_nt * G, p.shared_w ? 1 : p.L);
   return launch<MixWgradTraits>(p, grid, st);
 }
