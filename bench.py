@@ -284,7 +284,9 @@ def run_gpu_arm(args):
     counter = {"n": 0}
     kernels_per_call = {"b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1,
                         "b200sht_mix_forward": 1, "b200sht_mix_backward": 2, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
-                        "b200sht_bias_grad": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1}
+                        "b200sht_bias_grad": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1,
+                        # one-call entry points: fft + legendre + mix + legendre + fft / fft + legendre + dgrad + wgrad + legendre + fft
+                        "b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6}
     orig_call = _lib.call
 
     def counting_call(name, *a):

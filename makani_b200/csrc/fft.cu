@@ -276,11 +276,10 @@ __host__ __device__ constexpr int ct_bufstride() { return (skew<R0>(H) + 2) | 1;
 
 // stage of a compile-time plan: smem (skewed) -> smem (skewed), rows row0 .. row0 + RPT - 1
 template <int H, int R, int Ns, int R0, int TPG, int RPT>
-__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tw, int bufstride, int t, int row0) {
+__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tws /* [R][Ns]: W^(r k H/(Ns R)) */, int bufstride, int t, int row0) {
   constexpr int NB = H / R;
   for (int j = t; j < NB; j += TPG) {
     const int k = j % Ns;
-    const int tstep = k * (H / (Ns * R));
     const int j0 = (j - k) * R + k;
     float2 w[R];
     int si[R], di[R];
@@ -288,7 +287,7 @@ __device__ __forceinline__ void ct_stage(const float2* in, float2* out, const fl
     for (int r = 0; r < R; ++r) {
       si[r] = skew<R0>(j + r * NB);
       di[r] = skew<R0>(j0 + r * Ns);
-      if (Ns > 1 && r > 0) w[r] = tw[r * tstep];
+      if (Ns > 1 && r > 0) w[r] = tws[r * Ns + k];   // consecutive threads -> consecutive k: conflict-free
     }
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
@@ -301,12 +300,30 @@ __device__ __forceinline__ void ct_stage(const float2* in, float2* out, const fl
         if (Ns > 1 && r > 0) a = cmul(a, w[r]);
         v[r] = a;
       }
-      Butterfly<R>::run(v, tw, H);
+      Butterfly<R>::run(v, nullptr, H);
 #pragma unroll
       for (int r = 0; r < R; ++r) dst[di[r]] = v[r];
     }
   }
 }
+
+// per-stage twiddle tables in shared memory: tw1 [R1][R0] for the second stage (Ns = R0), tw2 [R2][R0*R1] for the third (Ns = R0*R1).
+// W_H^e = W_N^(2e) comes from the plan's length-N table.
+template <int R0, int R1, int R2>
+__device__ __forceinline__ void ct_build_twiddles(float2* tw1, float2* tw2, const float2* __restrict__ twN, int nthreads) {
+  constexpr int H = R0 * R1 * R2;
+  for (int i = threadIdx.x; i < R1 * R0; i += nthreads) {
+    const int r = i / R0, k = i - r * R0;
+    tw1[i] = twN[2 * (r * k * (H / (R0 * R1)))];
+  }
+  if (R2 > 1)
+    for (int i = threadIdx.x; i < R2 * R0 * R1; i += nthreads) {
+      const int r = i / (R0 * R1), k = i - r * (R0 * R1);
+      tw2[i] = twN[2 * (r * k)];
+    }
+}
+template <int R0, int R1, int R2>
+__host__ __device__ constexpr int ct_tw_elems() { return R1 * R0 + (R2 > 1 ? R2 * R0 * R1 : 0); }
 
 __device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* p) {
@@ -326,14 +343,15 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_analysis_ct_kernel(const T* 
   constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
   static_assert(ROWS % GROUPS == 0 && ROWS % 4 == 0, "row grouping");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tw = reinterpret_cast<float2*>(smem_raw);   // W_H^t = W_N^(2t)
-  float2* b0 = tw + H;
+  float2* tw1 = reinterpret_cast<float2*>(smem_raw);
+  float2* tw2 = tw1 + R1 * R0;
+  float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
   float2* b1 = b0 + ROWS * BS;
   const int k0 = blockIdx.x * ROWS;
   const int r = blockIdx.y;
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
   const int row0 = grp * RPT;
-  for (int i = threadIdx.x; i < H; i += THREADS) tw[i] = prm.twiddle[2 * i];
+  ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
 
   // ---- stage 0 fused with the global load
   {
@@ -359,11 +377,11 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_analysis_ct_kernel(const T* 
     }
   }
   __syncthreads();
-  ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw, BS, t, row0);
+  ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw1, BS, t, row0);
   __syncthreads();
   const float2* res = b1;
   if (R2 > 1) {
-    ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw, BS, t, row0);
+    ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw2, BS, t, row0);
     __syncthreads();
     res = b0;
   }
@@ -404,15 +422,17 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const fl
   constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
   constexpr int NsL = H / RL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tw = reinterpret_cast<float2*>(smem_raw);
-  float2* b0 = tw + H;
+  float2* tw1 = reinterpret_cast<float2*>(smem_raw);
+  float2* tw2 = tw1 + R1 * R0;
+  float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
   float2* b1 = b0 + ROWS * BS;
   const int k0 = blockIdx.x * ROWS;
   const int r = blockIdx.y;
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
   const int row0 = grp * RPT;
   const int mmax = prm.mmax;
-  for (int i = threadIdx.x; i < H; i += THREADS) tw[i] = prm.twiddle[2 * i];
+  ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
+  const float2* twL = (R2 > 1) ? tw2 : tw1;   // table of the last stage: [RL][NsL]
 
   // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re).
   // item = (q in [0, H/2], quad of 4 rows): reads X[q] and X[H-q] once, writes Z'[q] and Z'[H-q].
@@ -464,11 +484,11 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const fl
     }
   }
   __syncthreads();
-  ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, tw, BS, t, row0);
+  ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, nullptr, BS, t, row0);
   __syncthreads();
   const float2* src = b1;
   if (R2 > 1) {
-    ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw, BS, t, row0);
+    ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw1, BS, t, row0);
     __syncthreads();
     src = b0;
   }
@@ -482,7 +502,7 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const fl
 #pragma unroll
       for (int rr = 0; rr < RL; ++rr) {
         si[rr] = skew<R0>(j + rr * NsL);
-        if (rr > 0) w[rr] = tw[rr * j];   // k = j, H / (Ns * R) = 1
+        if (rr > 0) w[rr] = twL[rr * NsL + j];   // k = j
       }
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
@@ -495,7 +515,7 @@ __global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const fl
           if (rr > 0) a = cmul(a, w[rr]);
           v[rr] = a;
         }
-        Butterfly<RL>::run(v, tw, H);
+        Butterfly<RL>::run(v, nullptr, H);
         if (k0 + row < prm.nlat) {
           const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + row] : 1.f;
           T* rp = base + (size_t)row * N + 2 * j;
@@ -659,7 +679,7 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
 template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
 static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
   constexpr int H = R0 * R1 * R2;
-  constexpr size_t smem = sizeof(float2) * ((size_t)H + 2 * ROWS * ct_bufstride<H, R0>());
+  constexpr size_t smem = sizeof(float2) * ((size_t)ct_tw_elems<R0, R1, R2>() + 2 * ROWS * ct_bufstride<H, R0>());
   static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
   dim3 grid(ceil_div(pl->kp, ROWS), prm.R);
   if (dir == 0) {

@@ -635,7 +635,10 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
   const size_t smem = smem_bytes(p);
   if (smem > 232448) { set_error("umma: %zu bytes of shared memory needed", smem); return B200SHT_ERR_UNSUPPORTED; }
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int ctas = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  // static round-robin over tiles: an odd CTA count not divisible by 3 keeps tile-grid periods (2 l- or m-tiles, 3 or 6 n/k-tiles)
+  // from locking heavy tiles onto the same CTAs
+  int ctas = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  while (ctas > 1 && (ctas % 2 == 0 || ctas % 3 == 0)) --ctas;
   umma_kernel<T><<<ctas, kUmmaThreads, smem, st>>>(p);
   B200_CHECK_LAUNCH();
   return 0;

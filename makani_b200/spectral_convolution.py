@@ -104,6 +104,76 @@ class _MixPacked(torch.autograd.Function):
         return gx, gw, gcb, None, None, None, None, None, None, None, None, None
 
 
+class _SpectralConvOneCall(torch.autograd.Function):
+    """SpectralConv forward / backward through b200sht_spectral_conv_forward / _backward (include/b200sht.h)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        from .sht import _dtype_code
+        lib = _lib.load()
+        dev = x.device
+        B = x.shape[0]
+        pf, pi = mod.forward_transform.plan(dev), mod.inverse_transform.plan(dev)
+        prec = resolve_precision(mod.precision)
+        op = mod._op & 0xFF
+        if weight.dtype != torch.complex64:
+            raise B200ShtError(f"spectral weights must be complex64, got {weight.dtype}")
+        desc = _lib.ConvDesc(B, mod.in_channels, mod.out_channels, mod.num_groups, op, _dtype_code(x.dtype), prec)
+        dptr = ctypes.c_void_p(ctypes.addressof(desc))
+        wsb = int(lib.b200sht_spectral_conv_workspace_bytes(pf.handle, pi.handle, dptr))
+        if wsb < 0:
+            _lib.check(-1, "b200sht_spectral_conv_workspace_bytes")
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        L, M = mod.modes_lat_local, mod.modes_lon_local
+        if op in _DENSE_OPS:
+            wdev = mod._wcache.get(weight, op, L, M, mod.num_groups, mod.in_channels, mod.out_channels, prec)
+        else:
+            wdev = weight.detach().contiguous()
+        spec_saved = torch.empty(pf.spec_elems(B, mod.in_channels), dtype=torch.float32, device=dev)
+        y = torch.empty((B, mod.out_channels, pi.nlat, pi.nlon), dtype=x.dtype, device=dev)
+        res = torch.empty((B, mod.in_channels, pi.nlat, pi.nlon), dtype=x.dtype, device=dev) if mod.scale_residual else None
+        b32 = bias.detach().reshape(-1).to(torch.float32).contiguous() if bias is not None else None
+        _lib.call("b200sht_spectral_conv_forward", pf.handle, pi.handle, dptr, _ptr(x), _ptr(wdev), _ptr(b32), _ptr(y), _ptr(res), _ptr(spec_saved),
+                  _ptr(ws), _stream(dev))
+        ctx.save_for_backward(spec_saved, wdev)
+        ctx.meta = (pf, pi, (B, mod.in_channels, mod.out_channels, mod.num_groups, op, _dtype_code(x.dtype), prec), tuple(x.shape), x.dtype,
+                    tuple(weight.shape), None if bias is None else (tuple(bias.shape), bias.dtype), L, M, wsb)
+        return (y, res) if res is not None else y
+
+    @staticmethod
+    def backward(ctx, gy, gres=None):
+        spec_saved, wdev = ctx.saved_tensors
+        pf, pi, d, xshape, xdtype, wshape, binfo, L, M, wsb = ctx.meta
+        B, Ci, Co, G, op, dt, prec = d
+        lib = _lib.load()
+        dev = gy.device
+        gy = gy.contiguous().to(xdtype)
+        gres = gres.contiguous().to(xdtype) if gres is not None else None
+        desc = _lib.ConvDesc(*d)
+        dptr = ctypes.c_void_p(ctypes.addressof(desc))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], (binfo is not None and ctx.needs_input_grad[2])
+        gx = torch.empty(xshape, dtype=xdtype, device=dev) if need_x else None
+        gw_dev = None
+        if need_w:
+            if op in _DENSE_OPS:
+                gw_dev = torch.empty(int(lib.b200sht_mix_weight_elems(op, L, M, G, Ci, Co)), dtype=torch.float32, device=dev)
+            else:
+                gw_dev = torch.empty(wshape, dtype=torch.complex64, device=dev)
+        gb = torch.empty(Co, dtype=torch.float32, device=dev) if need_b else None
+        _lib.call("b200sht_spectral_conv_backward", pf.handle, pi.handle, dptr, _ptr(gy), _ptr(gres), _ptr(spec_saved), _ptr(wdev), _ptr(gx), _ptr(gw_dev),
+                  _ptr(gb), _ptr(ws), _stream(dev))
+        gw = None
+        if need_w:
+            if op in _DENSE_OPS:
+                gw = torch.empty(wshape, dtype=torch.complex64, device=dev)
+                _lib.call("b200sht_mix_weight_unpack", op, _ptr(gw_dev), _ptr(gw), L, G, Ci, Co, _stream(dev))
+            else:
+                gw = gw_dev
+        gbias = gb.reshape(binfo[0]).to(binfo[1]) if need_b else None
+        return gx, gw, gbias, None
+
+
 def mix_packed(spec, weight, op, L, M, B, G, Ci, Co, precision="auto", cbias=None, cache=None):
     return _MixPacked.apply(spec, weight, cbias, op, L, M, B, G, Ci, Co, resolve_precision(precision), cache)
 
@@ -189,6 +259,7 @@ class SpectralConv(nn.Module):
         if getattr(self.inverse_transform, "packed_dense", False):
             self._op |= _lib.DENSE_FLAG
         self._wcache = PackedWeightCache()
+        self.one_call = True   # False: one autograd node per stage (same kernels; used by the distributed transforms)
 
     def forward(self, x):
         dtype = x.dtype
@@ -196,6 +267,13 @@ class SpectralConv(nn.Module):
         xin = x if dtype in (torch.float32, torch.bfloat16) else x.to(torch.float32)
         out_dtype = xin.dtype
         B = xin.shape[0]
+        if self.one_call and isinstance(self.forward_transform, RealSHT) and isinstance(self.inverse_transform, InverseRealSHT):
+            # whole block through the two C-ABI entry points b200sht_spectral_conv_forward / _backward (2 host calls per step)
+            bias = self.bias if hasattr(self, "bias") else None
+            out = _SpectralConvOneCall.apply(xin.contiguous(), self.weight, bias, self)
+            if self.scale_residual:
+                return out[0].to(dtype), out[1].to(dtype)
+            return out.to(dtype), residual
         # transforms run in fp32/TF32 regardless of autocast, as the reference disables autocast around them (:237-241)
         xs = self.forward_transform.forward_packed(xin)
         if self.scale_residual:
