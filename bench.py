@@ -177,6 +177,43 @@ def cpu_reference_steps(wl, steps, warmup, act_dtype=torch.bfloat16):
     return sum(times) / len(times)
 
 
+def gpu_library_baseline(wl, act_dtype, dev, flush, steps=5):
+    """fwd+bwd of the block through torch.fft + torch.einsum ON THE GPU (what torch-harmonics + makani dispatch to: cuFFT, cuBLAS)."""
+    O, sht, isht = build_oracle_block(wl)
+    sht, isht = sht.to(dev), isht.to(dev)
+    nlat_i, nlon_i, _, nlat_o, nlon_o, _, L, M, C = WORKLOADS[wl]
+    torch.manual_seed(333)
+    w = (math.sqrt(1.0 / C) * torch.randn(1, C, C, L, dtype=torch.complex64, device=dev)).requires_grad_(True)
+    x = torch.randn(1, C, nlat_i, nlon_i, device=dev).to(act_dtype).requires_grad_(True)
+    gy = torch.randn(1, C, nlat_o, nlon_o, device=dev).to(act_dtype)
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        def step():
+            x.grad = None
+            w.grad = None
+            y, _ = O.spectral_conv_forward(x, w, sht, isht, operator_type="dhconv")
+            y.backward(gy)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        ms /= steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    return {"value": 1e3 / ms, "unit": "samples/s", "ms_per_step": ms,
+            "what": "same block through torch.fft + torch.einsum on this GPU (cuFFT + cuBLAS, allow_tf32=True, dense einsums incl. l<m zeros)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -390,6 +427,15 @@ def run_gpu_arm(args):
                "sample": f"1 warm-up + 1 timed full fwd+bwd step of {wl} through oracle/makani_oracle.py (torch.fft + torch.einsum fp32, {cores} threads "
                          f"chosen by calibration of {avail} available), {t:.2f} s/step"}
 
+    # The library path the reference runs on a GPU (cuFFT + cuBLAS einsum, allow_tf32=True as makani/train.py:87), timed on this
+    # B200 with the same restated modules (the real torch-harmonics is not installable): informational, never the product path.
+    lib = None
+    if not args.no_cpu:
+        try:
+            lib = gpu_library_baseline(wl, act_dtype, dev, flush)
+        except Exception as e:  # pragma: no cover
+            lib = {"error": str(e)[:200]}
+
     x_bytes = x_host.numel() * x_host.element_size()
     line = {
         "metric": "SFNO-block fwd+bwd samples/sec", "value": world * 1e3 / ms_dev, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -405,6 +451,7 @@ def run_gpu_arm(args):
         "roofline": roof,
         "roofline_stages": stages,
         "cpu_baseline": cpu,
+        "gpu_library_baseline": lib,
         "tflops_nnz": flops_fwd_bwd(wl) / (ms_dev * 1e-3) / 1e12,
     }
     print(json.dumps(line), flush=True)

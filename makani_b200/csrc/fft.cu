@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "fft_roots.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace b200sht {
@@ -335,195 +336,254 @@ __device__ __forceinline__ void st_pair(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2) for H = nlon / 2, R2 == 1 for two stages
-template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
-__global__ void __launch_bounds__(GROUPS * TPG) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
+// raw element pair as loaded from global memory (converted to float2 only when stage 0 consumes it)
+template <typename T> struct RawPair;
+template <> struct RawPair<float> {
+  float2 v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ float2 get() const { return v; }
+};
+template <> struct RawPair<__nv_bfloat16> {
+  unsigned int v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const unsigned int*>(p)); }
+  __device__ __forceinline__ void zero() { v = 0u; }
+  __device__ __forceinline__ float2 get() const { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
+};
+
+// x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2) for H = nlon / 2, R2 == 1 for two stages.
+// Persistent CTAs walk the (row group, image) tiles; the stage-0 operands of the NEXT tile are loaded into registers right after
+// stage 0 of the current one, so the HBM latency is hidden behind stages 1, 2 and the store pass.
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
+__global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
   constexpr int H = R0 * R1 * R2, N = 2 * H;
   constexpr int BS = ct_bufstride<H, R0>();
   constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
+  constexpr int NB0 = H / R0;
   static_assert(ROWS % GROUPS == 0 && ROWS % 4 == 0, "row grouping");
+  static_assert(NB0 <= TPG, "one stage-0 butterfly index per thread (register prefetch)");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
   float2* tw2 = tw1 + R1 * R0;
   float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
   float2* b1 = b0 + ROWS * BS;
-  const int k0 = blockIdx.x * ROWS;
-  const int r = blockIdx.y;
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
   const int row0 = grp * RPT;
+  const int ntx = (prm.kp + ROWS - 1) / ROWS;
+  const int ntiles = ntx * prm.R;
   ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
 
-  // ---- stage 0 fused with the global load
-  {
-    constexpr int NB = H / R0;
+  RawPair<T> raw[RPT][R0];
+  auto load_tile = [&](int tile) {
+    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
     const T* base = x + ((size_t)r * prm.nlat + k0) * N;
-    for (int j = t; j < NB; j += TPG) {
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      const int row = row0 + q;
+      const bool valid = (t < NB0) && (k0 + row) < prm.nlat;
+      const T* rp = base + (size_t)row * N + 2 * t;
+#pragma unroll
+      for (int rr = 0; rr < R0; ++rr) {
+        if (valid) raw[q][rr].load(rp + 2 * rr * NB0);
+        else raw[q][rr].zero();
+      }
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile);
+  __syncthreads();   // twiddle tables
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
+    // ---- stage 0 from the prefetched registers
+    if (t < NB0) {
       int di[R0];
 #pragma unroll
-      for (int rr = 0; rr < R0; ++rr) di[rr] = skew<R0>(j * R0 + rr);
+      for (int rr = 0; rr < R0; ++rr) di[rr] = skew<R0>(t * R0 + rr);
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
-        const int row = row0 + q;
-        const bool valid = (k0 + row) < prm.nlat;
-        const T* rp = base + (size_t)row * N + 2 * j;
         float2 v[R0];
 #pragma unroll
-        for (int rr = 0; rr < R0; ++rr) v[rr] = valid ? ld_pair(rp + 2 * rr * NB) : make_float2(0.f, 0.f);
+        for (int rr = 0; rr < R0; ++rr) v[rr] = raw[q][rr].get();
         Butterfly<R0>::run(v, nullptr, H);
-        float2* dst = b0 + row * BS;
+        float2* dst = b0 + (row0 + q) * BS;
 #pragma unroll
         for (int rr = 0; rr < R0; ++rr) dst[di[rr]] = v[rr];
       }
     }
-  }
-  __syncthreads();
-  ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw1, BS, t, row0);
-  __syncthreads();
-  const float2* res = b1;
-  if (R2 > 1) {
-    ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw2, BS, t, row0);
+    if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);   // in flight until the next iteration
     __syncthreads();
-    res = b0;
-  }
-
-  // ---- split + truncate + scale + store: item = (m, quad of 4 rows); two 16-byte stores (re, im) per item
-  constexpr int QUADS = ROWS / 4;
-  for (int e = threadIdx.x; e < prm.mmax * QUADS; e += THREADS) {
-    const int qd = e % QUADS, m = e / QUADS;
-    const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
-    const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
-    float re[4], imv[4];
+    ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw1, BS, t, row0);
+    __syncthreads();
+    const float2* res = b1;
+    if (R2 > 1) {
+      ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw2, BS, t, row0);
+      __syncthreads();
+      res = b0;
+    }
+    // ---- split + truncate + scale + store: item = (m, quad of 4 rows); two 16-byte stores (re, im) per item
+    constexpr int QUADS = ROWS / 4;
+    for (int e = threadIdx.x; e < prm.mmax * QUADS; e += THREADS) {
+      const int qd = e % QUADS, m = e / QUADS;
+      const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
+      const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
+      float re[4], imv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = qd * 4 + i;
-      const float2 Z = res[row * BS + im], Zc = res[row * BS + ic];
-      const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
-      const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
-      const float2 WO = cmul(wm, Od);
-      const float sc = mode_scale_analysis(prm, m, k0 + row);
-      re[i] = finish_analysis(prm, (E.x + WO.x) * sc);
-      imv[i] = finish_analysis(prm, (E.y + WO.y) * sc);
+      for (int i = 0; i < 4; ++i) {
+        const int row = qd * 4 + i;
+        const float2 Z = res[row * BS + im], Zc = res[row * BS + ic];
+        const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
+        const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
+        const float2 WO = cmul(wm, Od);
+        const float sc = mode_scale_analysis(prm, m, k0 + row);
+        re[i] = finish_analysis(prm, (E.x + WO.x) * sc);
+        imv[i] = finish_analysis(prm, (E.y + WO.y) * sc);
+      }
+      const int k = k0 + qd * 4;
+      if (k < prm.kp) {
+        float* dst = X + (((size_t)m * 2) * prm.R + r) * prm.kp + k;
+        *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
+        *reinterpret_cast<float4*>(dst + (size_t)prm.R * prm.kp) = make_float4(imv[0], imv[1], imv[2], imv[3]);
+      }
     }
-    const int k = k0 + qd * 4;
-    if (k < prm.kp) {
-      float* dst = X + (((size_t)m * 2) * prm.R + r) * prm.kp + k;
-      *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
-      *reinterpret_cast<float4*>(dst + (size_t)prm.R * prm.kp) = make_float4(imv[0], imv[1], imv[2], imv[3]);
-    }
+    __syncthreads();   // b0 / b1 are reused by the next tile
   }
 }
 
-// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]
-template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
-__global__ void __launch_bounds__(GROUPS * TPG) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
+// latspec [mmax][2][R][kp] -> y [R][nlat][nlon]   (persistent, with register prefetch of the next tile's spectrum)
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
+__global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
   constexpr int H = R0 * R1 * R2, N = 2 * H;
   constexpr int BS = ct_bufstride<H, R0>();
   constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
   constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
   constexpr int NsL = H / RL;
+  constexpr int QUADS = ROWS / 4;
+  constexpr int NITEMS = (H / 2 + 1) * QUADS;
+  constexpr int IPT = (NITEMS + THREADS - 1) / THREADS;   // spectrum-build items per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
   float2* tw2 = tw1 + R1 * R0;
   float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
   float2* b1 = b0 + ROWS * BS;
-  const int k0 = blockIdx.x * ROWS;
-  const int r = blockIdx.y;
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
   const int row0 = grp * RPT;
   const int mmax = prm.mmax;
+  const int ntx = (prm.kp + ROWS - 1) / ROWS;
+  const int ntiles = ntx * prm.R;
   ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
   const float2* twL = (R2 > 1) ? tw2 : tw1;   // table of the last stage: [RL][NsL]
 
-  // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re).
-  // item = (q in [0, H/2], quad of 4 rows): reads X[q] and X[H-q] once, writes Z'[q] and Z'[H-q].
-  constexpr int QUADS = ROWS / 4;
-  for (int e = threadIdx.x; e < (H / 2 + 1) * QUADS; e += THREADS) {
-    const int qd = e % QUADS, q = e / QUADS;
-    const int q2 = H - q;                                    // partner index (q2 == H for q == 0)
-    const int k = k0 + qd * 4;
-    float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f}, br[4] = {0.f, 0.f, 0.f, 0.f}, bi[4] = {0.f, 0.f, 0.f, 0.f};
-    if (k < prm.kp) {
-      if (q < mmax) {
-        const float* src = Zs + (((size_t)q * 2) * prm.R + r) * prm.kp + k;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp);
-        ar[0] = a.x; ar[1] = a.y; ar[2] = a.z; ar[3] = a.w; ai[0] = b.x; ai[1] = b.y; ai[2] = b.z; ai[3] = b.w;
-      }
-      if (q2 < mmax) {
-        const float* src = Zs + (((size_t)q2 * 2) * prm.R + r) * prm.kp + k;
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp);
-        br[0] = a.x; br[1] = a.y; br[2] = a.z; br[3] = a.w; bi[0] = b.x; bi[1] = b.y; bi[2] = b.z; bi[3] = b.w;
-      }
-    }
-    const bool a_self = (q == 0), b_self = (q2 == H);        // DC and Nyquist: imaginary part ignored, no halving
-    const float ha = (prm.scale_mode == 1 && !a_self) ? 0.5f : 1.f;
-    const float hb = (prm.scale_mode == 1 && !b_self) ? 0.5f : 1.f;
-    const float2 wq = __ldg(prm.twiddle + q);                 // W_N^q ; W_N^-q = conj
-    const float2 wq2 = (q2 < N) ? __ldg(prm.twiddle + (q2 % N)) : make_float2(1.f, 0.f);
+  // item = (q in [0, H/2], quad of 4 rows): X[q] and X[H-q] of 4 rows (re, im) = four 16-byte loads
+  float4 pa_r[IPT], pa_i[IPT], pb_r[IPT], pb_i[IPT];
+  auto load_tile = [&](int tile) {
+    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = qd * 4 + i;
-      const bool valid = (k + i) < prm.nlat;
-      float Ar = valid ? ar[i] * ha : 0.f, Ai = (valid && !a_self) ? ai[i] * ha : 0.f;   // A = X[q]
-      float Br = valid ? br[i] * hb : 0.f, Bi = (valid && !b_self) ? bi[i] * hb : 0.f;   // B = X[H-q]
-      // Z'[q] = (A + conj B) + i (A - conj B) conj(wq)
-      {
-        const float sr = Ar + Br, si2 = Ai - Bi;              // A + conj B
-        const float dr = Ar - Br, dii = Ai + Bi;              // A - conj B
-        const float tr = dr * wq.x + dii * wq.y, ti = dii * wq.x - dr * wq.y;   // (A - conj B) * conj(wq)
-        const float zr = sr - ti, zi = si2 + tr;              // + i * t
-        b0[row * BS + skew<R0>(q)] = make_float2(zi, zr);
-      }
-      if (q != 0 && q2 != q) {
-        // Z'[q2] = (B + conj A) + i (B - conj A) conj(wq2)
-        const float sr = Br + Ar, si2 = Bi - Ai;
-        const float dr = Br - Ar, dii = Bi + Ai;
-        const float tr = dr * wq2.x + dii * wq2.y, ti = dii * wq2.x - dr * wq2.y;
-        const float zr = sr - ti, zi = si2 + tr;
-        b0[row * BS + skew<R0>(q2)] = make_float2(zi, zr);
+    for (int it = 0; it < IPT; ++it) {
+      const int e = threadIdx.x + it * THREADS;
+      const int qd = e % QUADS, q = e / QUADS, q2 = H - q;
+      const int k = k0 + qd * 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      pa_r[it] = z; pa_i[it] = z; pb_r[it] = z; pb_i[it] = z;
+      if (e < NITEMS && k < prm.kp) {
+        if (q < mmax) {
+          const float* src = Zs + (((size_t)q * 2) * prm.R + r) * prm.kp + k;
+          pa_r[it] = __ldg(reinterpret_cast<const float4*>(src));
+          pa_i[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp));
+        }
+        if (q2 < mmax) {
+          const float* src = Zs + (((size_t)q2 * 2) * prm.R + r) * prm.kp + k;
+          pb_r[it] = __ldg(reinterpret_cast<const float4*>(src));
+          pb_i[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp));
+        }
       }
     }
-  }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) load_tile(tile);
   __syncthreads();
-  ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, nullptr, BS, t, row0);
-  __syncthreads();
-  const float2* src = b1;
-  if (R2 > 1) {
-    ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw1, BS, t, row0);
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
+    // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re)
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) {
+      const int e = threadIdx.x + it * THREADS;
+      if (e >= NITEMS) continue;
+      const int qd = e % QUADS, q = e / QUADS;
+      const int q2 = H - q;                                    // partner index (q2 == H for q == 0)
+      const int k = k0 + qd * 4;
+      const float ar[4] = {pa_r[it].x, pa_r[it].y, pa_r[it].z, pa_r[it].w}, ai[4] = {pa_i[it].x, pa_i[it].y, pa_i[it].z, pa_i[it].w};
+      const float br[4] = {pb_r[it].x, pb_r[it].y, pb_r[it].z, pb_r[it].w}, bi[4] = {pb_i[it].x, pb_i[it].y, pb_i[it].z, pb_i[it].w};
+      const bool a_self = (q == 0), b_self = (q2 == H);        // DC and Nyquist: imaginary part ignored, no halving
+      const float ha = (prm.scale_mode == 1 && !a_self) ? 0.5f : 1.f;
+      const float hb = (prm.scale_mode == 1 && !b_self) ? 0.5f : 1.f;
+      const float2 wq = __ldg(prm.twiddle + q);                 // W_N^q ; W_N^-q = conj
+      const float2 wq2 = __ldg(prm.twiddle + q2);               // q2 <= H < N
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = qd * 4 + i;
+        const bool valid = (k + i) < prm.nlat;
+        const float Ar = valid ? ar[i] * ha : 0.f, Ai = (valid && !a_self) ? ai[i] * ha : 0.f;   // A = X[q]
+        const float Br = valid ? br[i] * hb : 0.f, Bi = (valid && !b_self) ? bi[i] * hb : 0.f;   // B = X[H-q]
+        {
+          const float sr = Ar + Br, si2 = Ai - Bi;              // A + conj B
+          const float dr = Ar - Br, dii = Ai + Bi;              // A - conj B
+          const float tr = dr * wq.x + dii * wq.y, ti = dii * wq.x - dr * wq.y;   // (A - conj B) * conj(wq)
+          b0[row * BS + skew<R0>(q)] = make_float2(si2 + tr, sr - ti);            // Z'[q] = s + i t, stored (im, re)
+        }
+        if (q != 0 && q2 != q) {
+          const float sr = Br + Ar, si2 = Bi - Ai;
+          const float dr = Br - Ar, dii = Bi + Ai;
+          const float tr = dr * wq2.x + dii * wq2.y, ti = dii * wq2.x - dr * wq2.y;
+          b0[row * BS + skew<R0>(q2)] = make_float2(si2 + tr, sr - ti);
+        }
+      }
+    }
+    if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);   // in flight until the next iteration
     __syncthreads();
-    src = b0;
-  }
-  // ---- last stage fused with the store: butterfly j yields z[e], e = j + rr * NsL, and (x[2e], x[2e+1]) = (Im, Re) of the swapped result
-  {
-    T* base = y + ((size_t)r * prm.nlat + k0) * N;
-    const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
-    for (int j = t; j < NsL; j += TPG) {
-      float2 w[RL];
-      int si[RL];
-#pragma unroll
-      for (int rr = 0; rr < RL; ++rr) {
-        si[rr] = skew<R0>(j + rr * NsL);
-        if (rr > 0) w[rr] = twL[rr * NsL + j];   // k = j
-      }
-#pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-        const int row = row0 + q;
-        const float2* s = src + row * BS;
-        float2 v[RL];
+    ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, nullptr, BS, t, row0);
+    __syncthreads();
+    const float2* src = b1;
+    if (R2 > 1) {
+      ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw1, BS, t, row0);
+      __syncthreads();
+      src = b0;
+    }
+    // ---- last stage fused with the store: butterfly j yields z[e], e = j + rr * NsL, (x[2e], x[2e+1]) = (Im, Re) of the swapped result
+    {
+      T* base = y + ((size_t)r * prm.nlat + k0) * N;
+      const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
+      for (int j = t; j < NsL; j += TPG) {
+        float2 w[RL];
+        int si[RL];
 #pragma unroll
         for (int rr = 0; rr < RL; ++rr) {
-          float2 a = s[si[rr]];
-          if (rr > 0) a = cmul(a, w[rr]);
-          v[rr] = a;
+          si[rr] = skew<R0>(j + rr * NsL);
+          if (rr > 0) w[rr] = twL[rr * NsL + j];   // k = j
         }
-        Butterfly<RL>::run(v, nullptr, H);
-        if (k0 + row < prm.nlat) {
-          const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + row] : 1.f;
-          T* rp = base + (size_t)row * N + 2 * j;
 #pragma unroll
-          for (int rr = 0; rr < RL; ++rr) st_pair(rp + 2 * rr * NsL, v[rr].y * sc + bias, v[rr].x * sc + bias);
+        for (int q = 0; q < RPT; ++q) {
+          const int row = row0 + q;
+          const float2* sp = src + row * BS;
+          float2 v[RL];
+#pragma unroll
+          for (int rr = 0; rr < RL; ++rr) {
+            float2 a = sp[si[rr]];
+            if (rr > 0) a = cmul(a, w[rr]);
+            v[rr] = a;
+          }
+          Butterfly<RL>::run(v, nullptr, H);
+          if (k0 + row < prm.nlat) {
+            const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + row] : 1.f;
+            T* rp = base + (size_t)row * N + 2 * j;
+#pragma unroll
+            for (int rr = 0; rr < RL; ++rr) st_pair(rp + 2 * rr * NsL, v[rr].y * sc + bias, v[rr].x * sc + bias);
+          }
         }
       }
     }
+    __syncthreads();   // b0 / b1 are reused by the next tile
   }
 }
 
@@ -676,18 +736,24 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
   return prm;
 }
 
-template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2>
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
 static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
   constexpr int H = R0 * R1 * R2;
   constexpr size_t smem = sizeof(float2) * ((size_t)ct_tw_elems<R0, R1, R2>() + 2 * ROWS * ct_bufstride<H, R0>());
   static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
-  dim3 grid(ceil_div(pl->kp, ROWS), prm.R);
+  // persistent CTAs: as many as fit concurrently (by shared memory), each walks tiles blockIdx.x, + gridDim.x, ...
+  const int ntiles = ceil_div(pl->kp, ROWS) * prm.R;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  dim3 grid(ntiles < per_sm * sms ? ntiles : per_sm * sms);
   if (dir == 0) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
   } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
+    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
   }
   B200_CHECK_LAUNCH();
   return 0;
@@ -695,22 +761,22 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
 
 // lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
 // i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
-#define CT_PLANS(X)          \
-  X(8, 4, 96, 8, 10, 9)      /* nlon 1440 */ \
-  X(8, 4, 96, 8, 9, 5)       /* nlon  720 */ \
-  X(8, 4, 64, 8, 6, 5)       /* nlon  480 */ \
-  X(8, 4, 64, 4, 9, 5)       /* nlon  360 */ \
-  X(8, 4, 64, 8, 5, 3)       /* nlon  240 */ \
-  X(8, 4, 64, 2, 9, 5)       /* nlon  180 */ \
-  X(8, 4, 32, 8, 3, 3)       /* nlon  144 */ \
-  X(8, 8, 32, 4, 4, 4)       /* nlon  128 */ \
-  X(8, 8, 32, 4, 4, 3)       /* nlon   96 */ \
-  X(8, 8, 32, 4, 3, 3)       /* nlon   72 */ \
-  X(8, 8, 32, 4, 8, 1)       /* nlon   64 */ \
-  X(8, 4, 32, 8, 4, 4)       /* nlon  256 */ \
-  X(8, 4, 64, 8, 8, 4)       /* nlon  512 */ \
-  X(8, 4, 64, 8, 8, 8)       /* nlon 1024 */ \
-  X(8, 2, 160, 16, 10, 9)    /* nlon 2880 */
+#define CT_PLANS(X)             \
+  X(8, 4, 96, 8, 10, 9, 2)      /* nlon 1440 */ \
+  X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
+  X(8, 4, 64, 8, 6, 5, 2)       /* nlon  480 */ \
+  X(8, 4, 64, 4, 9, 5, 2)       /* nlon  360 */ \
+  X(8, 4, 64, 8, 5, 3, 2)       /* nlon  240 */ \
+  X(8, 4, 64, 2, 9, 5, 2)       /* nlon  180 */ \
+  X(8, 4, 32, 8, 3, 3, 2)       /* nlon  144 */ \
+  X(8, 8, 32, 4, 4, 4, 2)       /* nlon  128 */ \
+  X(8, 8, 32, 4, 4, 3, 2)       /* nlon   96 */ \
+  X(8, 8, 32, 4, 3, 3, 2)       /* nlon   72 */ \
+  X(8, 8, 32, 4, 8, 1, 2)       /* nlon   64 */ \
+  X(8, 4, 32, 8, 4, 4, 2)       /* nlon  256 */ \
+  X(8, 4, 64, 8, 8, 4, 2)       /* nlon  512 */ \
+  X(8, 4, 64, 8, 8, 8, 2)       /* nlon 1024 */ \
+  X(8, 2, 160, 16, 10, 9, 1)    /* nlon 2880 */
 
 template <typename T>
 static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st, bool* handled) {
@@ -718,8 +784,11 @@ static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const
   // the compile-time plans move element pairs / quads with vector loads: both tensors must be 16-byte aligned
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return 0;
   *handled = true;
-#define X(RW, G, TP, A, B_, C_) \
-  if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_>(pl, dir, in, out, prm, st);
+  // experiment switch (B200SHT_FFT_VARIANT=1): 1440-point rows with 2 thread groups x 4 rows per thread instead of 4 x 2
+  static const int variant = [] { const char* e = getenv("B200SHT_FFT_VARIANT"); return e ? atoi(e) : 0; }();
+  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
+#define X(RW, G, TP, A, B_, C_, MB) \
+  if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_, MB>(pl, dir, in, out, prm, st);
   CT_PLANS(X)
 #undef X
   *handled = false;
