@@ -415,8 +415,22 @@ def run_gpu_arm(args):
     roof = None
     if stages:
         top = max(stages, key=lambda k: stages[k]["ms"])
+        # DRAM bytes per launch of that kernel from the last committed ncu --set full capture (profiles/traffic.json)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            fam = {"fft_analysis": "fft_analysis_ct_kernel", "fft_synthesis": "fft_synthesis_ct_kernel", "legendre_analysis": "umma_kernel<AnaTraits>",
+                   "legendre_synthesis": "umma_kernel<SynTraits>", "mix_forward": "umma_kernel<MixFwdTraits>", "mix_backward": "umma_kernel<MixDgradTraits>"}
+            key = next((v for k, v in fam.items() if top.startswith(k)), None)
+            for name, rec in tj.items():
+                if key and key in name:
+                    traffic = rec["dram_bytes_per_launch"]
+                    break
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": top, "achieved": stages[top]["GBps"], "peak": peak, "unit": "GB/s", "frac": round(stages[top]["GBps"] / peak, 4),
-                "traffic": None, "peak_source": peak_src, "kernel_ms": stages[top]["ms"], "sum_stage_ms": round(sum(s["ms"] for s in stages.values()), 3)}
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": stages[top]["ms"], "sum_stage_ms": round(sum(s["ms"] for s in stages.values()), 3)}
 
     # CPU baseline beside it (bounded sample: 1 warm-up + 2 timed steps of the same workload)
     cpu = None

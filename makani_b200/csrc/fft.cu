@@ -421,29 +421,43 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
       __syncthreads();
       res = b0;
     }
-    // ---- split + truncate + scale + store: item = (m, quad of 4 rows); two 16-byte stores (re, im) per item
-    constexpr int QUADS = ROWS / 4;
-    for (int e = threadIdx.x; e < prm.mmax * QUADS; e += THREADS) {
-      const int qd = e % QUADS, m = e / QUADS;
-      const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
-      const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
-      float re[4], imv[4];
+    // ---- split + truncate + scale + store: a thread owns one quad of 4 rows and walks the orders m; two 16-byte stores per (m, quad)
+    {
+      constexpr int QUADS = ROWS / 4;
+      static_assert(THREADS % QUADS == 0, "quad ownership");
+      const int qd = threadIdx.x % QUADS;
+      float rsc[4];   // per-row factor: quadrature weight (SHT forward) or 1 (adjoint of irfft), 0 in the latitude padding
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int row = qd * 4 + i;
-        const float2 Z = res[row * BS + im], Zc = res[row * BS + ic];
-        const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
-        const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
-        const float2 WO = cmul(wm, Od);
-        const float sc = mode_scale_analysis(prm, m, k0 + row);
-        re[i] = finish_analysis(prm, (E.x + WO.x) * sc);
-        imv[i] = finish_analysis(prm, (E.y + WO.y) * sc);
+        const int k = k0 + qd * 4 + i;
+        rsc[i] = (k < prm.nlat) ? (prm.scale_mode == 0 ? prm.rowscale[k] : 1.f) : 0.f;
       }
-      const int k = k0 + qd * 4;
-      if (k < prm.kp) {
-        float* dst = X + (((size_t)m * 2) * prm.R + r) * prm.kp + k;
-        *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
-        *reinterpret_cast<float4*>(dst + (size_t)prm.R * prm.kp) = make_float4(imv[0], imv[1], imv[2], imv[3]);
+      const float2* rb = res + (qd * 4) * BS;
+      const int kq = k0 + qd * 4;
+      float* xbase = X + (size_t)r * prm.kp + kq;
+      const size_t mstride = (size_t)2 * prm.R * prm.kp, pstride = (size_t)prm.R * prm.kp;
+      const bool rnd = prm.round_tf32 != 0;
+      for (int m = threadIdx.x / QUADS; m < prm.mmax; m += THREADS / QUADS) {
+        const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
+        const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
+        const float msc = (prm.scale_mode == 1 && !(m == 0 || 2 * m == N)) ? 2.f : 1.f;
+        float re[4], imv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 Z = rb[i * BS + im], Zc = rb[i * BS + ic];
+          const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
+          const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
+          const float2 WO = cmul(wm, Od);
+          const float sc = rsc[i] * msc;
+          const float a = (E.x + WO.x) * sc, b = (E.y + WO.y) * sc;
+          re[i] = rnd ? tf32_rn(a) : a;
+          imv[i] = rnd ? tf32_rn(b) : b;
+        }
+        if (kq < prm.kp) {
+          float* dst = xbase + (size_t)m * mstride;
+          *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
+          *reinterpret_cast<float4*>(dst + pstride) = make_float4(imv[0], imv[1], imv[2], imv[3]);
+        }
       }
     }
     __syncthreads();   // b0 / b1 are reused by the next tile
@@ -762,7 +776,7 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
 // lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
 // i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
 #define CT_PLANS(X)             \
-  X(8, 4, 96, 8, 10, 9, 2)      /* nlon 1440 */ \
+  X(8, 2, 96, 8, 10, 9, 2)      /* nlon 1440: 2 groups x 4 rows per thread (no spills at 2 CTAs/SM; measured faster than 4 x 2) */ \
   X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
   X(8, 4, 64, 8, 6, 5, 2)       /* nlon  480 */ \
   X(8, 4, 64, 4, 9, 5, 2)       /* nlon  360 */ \
@@ -784,9 +798,9 @@ static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const
   // the compile-time plans move element pairs / quads with vector loads: both tensors must be 16-byte aligned
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return 0;
   *handled = true;
-  // experiment switch (B200SHT_FFT_VARIANT=1): 1440-point rows with 2 thread groups x 4 rows per thread instead of 4 x 2
+  // experiment switch (B200SHT_FFT_VARIANT=1): 1440-point rows with 4 thread groups x 2 rows per thread
   static const int variant = [] { const char* e = getenv("B200SHT_FFT_VARIANT"); return e ? atoi(e) : 0; }();
-  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
+  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 4, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
 #define X(RW, G, TP, A, B_, C_, MB) \
   if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_, MB>(pl, dir, in, out, prm, st);
   CT_PLANS(X)

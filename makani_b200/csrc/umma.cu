@@ -419,15 +419,31 @@ struct MixFwdTraits {
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + n0, vr);
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.N + n0, vi);
       if (!row_ok) continue;
+      // 16-byte stores (one row per thread: a warp store touches 32 rows, so wide stores cut the L2 write transactions 4x)
+      const bool vec_ok = (((g * NOg) & 3) == 0);   // cp_out and o0 + n0 are multiples of 4
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int o = o0 + n0 + q;
-        if (o >= limit) break;
-        float a = vr[q], c = vi[q];
-        if (o >= NOg) { a = 0.f; c = 0.f; }
-        else if (with_bias) { const float2 cb = p.cbias[g * NOg + o]; a += cb.x; c += cb.y; }
-        yr[o] = tf32_rn(a);
-        yi[o] = tf32_rn(c);
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const int ob = o0 + n0 + q4 * 4;
+        if (ob >= limit) break;
+        float a[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int o = ob + u;
+          a[u] = vr[q4 * 4 + u];
+          c[u] = vi[q4 * 4 + u];
+          if (o >= NOg) { a[u] = 0.f; c[u] = 0.f; }
+          else if (with_bias) { const float2 cb = p.cbias[g * NOg + o]; a[u] += cb.x; c[u] += cb.y; }
+          a[u] = tf32_rn(a[u]);
+          c[u] = tf32_rn(c[u]);
+        }
+        if (vec_ok && ob + 3 < limit) {
+          *reinterpret_cast<float4*>(yr + ob) = make_float4(a[0], a[1], a[2], a[3]);
+          *reinterpret_cast<float4*>(yi + ob) = make_float4(c[0], c[1], c[2], c[3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ob + u < limit) { yr[ob + u] = a[u]; yi[ob + u] = c[u]; }
+        }
       }
     }
   }
@@ -525,11 +541,17 @@ struct MixWgradTraits {
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + p.N + n0, vi);
       if (!ok) continue;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int o = t.o0 + n0 + q;
-        if (o >= p.cop) break;
-        row[o] = (o < p.Cog) ? vr[q] : 0.f;
-        row[p.cop + o] = (o < p.Cog) ? vi[q] : 0.f;
+      for (int q4 = 0; q4 < 8; ++q4) {   // cop is a multiple of 4: whole float4 groups, 16-byte aligned
+        const int ob = t.o0 + n0 + q4 * 4;
+        if (ob >= p.cop) break;
+        float a[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = (ob + u < p.Cog) ? vr[q4 * 4 + u] : 0.f;
+          c[u] = (ob + u < p.Cog) ? vi[q4 * 4 + u] : 0.f;
+        }
+        *reinterpret_cast<float4*>(row + ob) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(row + p.cop + ob) = make_float4(c[0], c[1], c[2], c[3]);
       }
     }
   }

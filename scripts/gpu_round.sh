@@ -10,7 +10,7 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload sfno_block_240x480x384 > gpurun_out/bench_2a.json 2>> gpurun_out/bench.err
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload sfno_block_721to240x384 > gpurun_out/bench_2b.json 2>> gpurun_out/bench.err
-B200SHT_FFT_VARIANT=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu > gpurun_out/bench_v1.json 2>> gpurun_out/bench.err
+
 if [ "$1" == "profile" ]; then bash scripts/gpu_profile.sh; fi
 echo "=== diag"; grep -E "failures|rc=1" gpurun_out/umma_diag.log | cut -c1-260 | tail -20
 echo "=== pytest"; grep -E "FAILED|passed|failed" gpurun_out/pytest_gpu.log | cut -c1-200; echo "=== pytest umma"; grep -E "FAILED|passed|failed|parity" gpurun_out/pytest_umma.log | cut -c1-220 | tail -40

@@ -91,6 +91,23 @@ def main():
                       f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {g('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active')} | "
                       f"{g('sm__warps_active.avg.pct_of_peak_sustained_active')} | {g('smsp__issue_active.avg.pct_of_peak_sustained_active')} | {g('launch__registers_per_thread')} | {d['top_stalls']} |")
         md.append("")
+    # DRAM traffic per launch of each captured kernel family -> profiles/traffic.json (bench.py fills roofline.traffic from it)
+    if allrows:
+        traffic = {}
+        for d in allrows:
+            try:
+                rd = float(d.get("dram__bytes_read.sum", "0 x").split(" ")[0].replace(",", ""))
+                wr = float(d.get("dram__bytes_write.sum", "0 x").split(" ")[0].replace(",", ""))
+                unit = d.get("dram__bytes_read.sum", "0 Mbyte").split(" ")[1]
+            except (ValueError, IndexError):
+                continue
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1e6)
+            name = d["kernel"].split("(")[0].replace("void ", "").strip()
+            traffic.setdefault(name, []).append((rd + wr) * mult)
+        out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v), "capture": tag} for k, v in traffic.items()}
+        with open(os.path.join(PROF, "traffic.json"), "w") as f:
+            json.dump(out, f, indent=1)
+
     bj = os.path.join(OUT, "bench.json")
     if os.path.exists(bj):
         try:
