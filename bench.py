@@ -347,14 +347,14 @@ def run_gpu_arm(args):
             sampler.start()
             t_wait = time.perf_counter()
             while not sampler.lines and time.perf_counter() - t_wait < 5.0:
-                dp_step()
+                step(x_dev)  # local load only: no collective here, the other ranks are waiting at the next barrier
                 torch.cuda.synchronize()
         ms_dev = timed(dp_step, args.steps, args.warmup)
         if sampler:
             n_before = len(sampler.lines)
             t_wait = time.perf_counter()
             while len(sampler.lines) < n_before + 2 and time.perf_counter() - t_wait < 1.0:  # one more sample under the same load
-                dp_step()
+                step(x_dev)
                 torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), use_flush=True)

@@ -11,7 +11,9 @@ timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2> gpu
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload sfno_block_240x480x384 > gpurun_out/bench_2a.json 2>> gpurun_out/bench.err
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --workload sfno_block_721to240x384 > gpurun_out/bench_2b.json 2>> gpurun_out/bench.err
 
+[ -x scripts/micro/f32x2 ] && timeout 120 scripts/micro/f32x2 > gpurun_out/micro_f32x2.log 2>&1
 if [ "$1" == "profile" ]; then bash scripts/gpu_profile.sh; fi
+echo "=== micro"; cat gpurun_out/micro_f32x2.log 2>/dev/null
 echo "=== diag"; grep -E "failures|rc=1" gpurun_out/umma_diag.log | cut -c1-260 | tail -20
 echo "=== pytest"; grep -E "FAILED|passed|failed" gpurun_out/pytest_gpu.log | cut -c1-200; echo "=== pytest umma"; grep -E "FAILED|passed|failed|parity" gpurun_out/pytest_umma.log | cut -c1-220 | tail -40
 echo "=== smoke"; tail -3 gpurun_out/smoke.log; echo "=== bench"; cat gpurun_out/bench.json | cut -c1-2500; tail -5 gpurun_out/bench.err
