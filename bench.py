@@ -287,6 +287,39 @@ def run_gpu_arm(args):
             dist.all_reduce(torch.view_as_real(conv.weight.grad))
         gw_host.copy_(conv.weight.grad, non_blocking=True)
 
+    feed = mb.HostFeed(x_host.shape, act_dtype, dev)
+
+    def e2e_pipelined(steps):
+        """K steps through HostFeed: the H2D copy of step i+1 and the read-back of step i-1 overlap the kernels of step i.
+        Returns ms per step (device clock, first push .. last read-back)."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        feed.h2d.wait_event(e0)          # the first copy starts inside the timed region
+        feed.push(x_host)
+        for i in range(steps):
+            xd = feed.pop()
+            if i + 1 < steps:
+                feed.push(x_host)
+            step(xd)
+            feed.release(xd)
+            if world > 1:
+                dist.all_reduce(torch.view_as_real(conv.weight.grad))
+            feed.read_back(conv.weight.grad, gw_host)
+        feed.drain()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+
     def timed(fn, steps, warmup, use_flush=True):
         for _ in range(warmup):
             fn()
@@ -357,7 +390,9 @@ def run_gpu_arm(args):
                 step(x_dev)
                 torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
-        ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), use_flush=True)
+        ms_e2e_serial = timed(step_e2e, args.steps, max(1, args.warmup // 2), use_flush=True)
+        e2e_pipelined(max(2, args.warmup))      # warm-up of the pipelined loop (allocator, streams)
+        ms_e2e = e2e_pipelined(args.steps)
     finally:
         _lib.call = orig_call
 
@@ -460,7 +495,12 @@ def run_gpu_arm(args):
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); inputs 151 MB > 126 MB L2",
                    "weight_relayout_in_step": True, "flops_fwd_bwd_nnz": flops_fwd_bwd(wl)},
         "clocks": clocks,
-        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": gw_host.numel() * 8},
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": gw_host.numel() * 8,
+                "how": "makani_b200.HostFeed: every step copies its 151 MB input from pinned host memory and reads its weight gradient back; the copy of "
+                       "step i+1 (side stream, second device buffer) and the read-back of step i-1 overlap the kernels of step i; K steps timed from the "
+                       "first copy to the last read-back; inputs span 2 x 151 MB > L2",
+                "serial_value": world * 1e3 / ms_e2e_serial, "serial_ms_per_step": ms_e2e_serial,
+                "serial_how": "copy -> fwd+bwd -> read-back in one stream, L2 flushed between steps"},
         "gpu_launches": launches_per_step,
         "roofline": roof,
         "roofline_stages": stages,

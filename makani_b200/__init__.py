@@ -6,10 +6,12 @@ Public surface (mirrors the reference):
     quadrature                                 <- torch_harmonics.quadrature
     distributed                                <- torch_harmonics.distributed (h x w spatial model parallelism)
     install_torch_harmonics_shim()             <- makes `import torch_harmonics` resolve to this package
+    HostFeed                                   <- double-buffered host->device input staging (the data loader's prefetch queue)
 """
 from ._lib import B200ShtError, load as load_library  # noqa: F401
 from . import quadrature  # noqa: F401
 from .sht import RealSHT, InverseRealSHT, get_plan, resolve_precision  # noqa: F401
 from .spectral_convolution import SpectralConv, SpectralAttention, ComplexReLU, mix_packed  # noqa: F401
+from .host_pipeline import HostFeed  # noqa: F401
 
 __version__ = "0.1.0"

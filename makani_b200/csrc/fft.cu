@@ -17,7 +17,7 @@
 // The stage / butterfly code is __host__ __device__ so that the same arithmetic is unit-tested on the CPU
 // (b200sht_debug_fft_host) without a GPU.
 #include "common.cuh"
-#include "fft_roots.cuh"
+#include "fft_butterfly.cuh"
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -62,138 +62,7 @@ bool make_fft_plan(int N, FftPlan* p) {
   return true;
 }
 
-// ------------------------------------------------------------------------------------------ butterflies
-HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-HD float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
-
-template <int R>
-struct Butterfly;
-
-template <>
-struct Butterfly<2> {
-  HD static void run(float2* v, const float2*, int) {
-    float2 a = v[0], b = v[1];
-    v[0] = cadd(a, b);
-    v[1] = csub(a, b);
-  }
-};
-
-HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
-  a0 = cadd(t0, t2);
-  a2 = csub(t0, t2);
-  a1 = cadd(t1, t3);
-  a3 = csub(t1, t3);
-}
-
-template <>
-struct Butterfly<4> {
-  HD static void run(float2* v, const float2*, int) { dft4(v[0], v[1], v[2], v[3]); }
-};
-
-template <>
-struct Butterfly<8> {
-  HD static void run(float2* v, const float2*, int) {
-    const float h = 0.70710678118654752440f;
-    float2 b0 = cadd(v[0], v[4]), b4 = csub(v[0], v[4]);
-    float2 b1 = cadd(v[1], v[5]), b5 = csub(v[1], v[5]);
-    float2 b2 = cadd(v[2], v[6]), b6 = csub(v[2], v[6]);
-    float2 b3 = cadd(v[3], v[7]), b7 = csub(v[3], v[7]);
-    // twiddles W8^1 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2
-    b5 = make_float2(h * (b5.x + b5.y), h * (b5.y - b5.x));
-    b6 = cmul_mi(b6);
-    b7 = make_float2(h * (b7.y - b7.x), -h * (b7.x + b7.y));
-    dft4(b0, b1, b2, b3);  // even outputs X[0], X[2], X[4], X[6]
-    dft4(b4, b5, b6, b7);  // odd outputs  X[1], X[3], X[5], X[7]
-    v[0] = b0; v[2] = b1; v[4] = b2; v[6] = b3;
-    v[1] = b4; v[3] = b5; v[5] = b6; v[7] = b7;
-  }
-};
-
-template <>
-struct Butterfly<3> {
-  HD static void run(float2* v, const float2*, int) {
-    const float s = 0.86602540378443864676f;
-    float2 t = cadd(v[1], v[2]), u = csub(v[1], v[2]);
-    float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
-    float2 w = make_float2(s * u.y, -s * u.x);  // -i * s * u
-    v[0] = cadd(v[0], t);
-    v[1] = cadd(m, w);
-    v[2] = csub(m, w);
-  }
-};
-
-template <>
-struct Butterfly<5> {
-  HD static void run(float2* v, const float2*, int) {
-    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-    float2 m1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-    float2 m2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-    float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-    v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-    float2 in1 = cmul_mi(n1), in2 = cmul_mi(n2);  // -i n
-    v[1] = cadd(m1, in1);
-    v[4] = csub(m1, in1);
-    v[2] = cadd(m2, in2);
-    v[3] = csub(m2, in2);
-  }
-};
-
-// generic O(R^2) butterfly for the rare odd primes (twiddles from the length-N table; R | N)
-template <int R>
-struct Butterfly {
-  HD static void run(float2* v, const float2* tw, int N) {
-    float2 o[R];
-    const int step = N / R;
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-      float2 acc = v[0];
-#pragma unroll
-      for (int r = 1; r < R; ++r) acc = cadd(acc, cmul(v[r], tw[((r * q) % R) * step]));
-      o[q] = acc;
-    }
-#pragma unroll
-    for (int q = 0; q < R; ++q) v[q] = o[q];
-  }
-};
-
-// Cooley-Tukey composite in registers: R = R1 * R2, input index n = R2 n1 + n2, output index k = k1 + R1 k2.
-template <int R1, int R2>
-struct Composite {
-  HD static void run(float2* v) {
-    constexpr int R = R1 * R2;
-    float2 t[R];
-#pragma unroll
-    for (int n2 = 0; n2 < R2; ++n2) {
-      float2 u[R1];
-#pragma unroll
-      for (int n1 = 0; n1 < R1; ++n1) u[n1] = v[R2 * n1 + n2];
-      Butterfly<R1>::run(u, nullptr, 0);
-#pragma unroll
-      for (int k1 = 0; k1 < R1; ++k1) t[n2 * R1 + k1] = (n2 * k1 == 0) ? u[k1] : cmul(u[k1], unit_root<R>(n2 * k1));
-    }
-#pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) {
-      float2 u[R2];
-#pragma unroll
-      for (int n2 = 0; n2 < R2; ++n2) u[n2] = t[n2 * R1 + k1];
-      Butterfly<R2>::run(u, nullptr, 0);
-#pragma unroll
-      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = u[k2];
-    }
-  }
-};
-template <> struct Butterfly<6> { HD static void run(float2* v, const float2*, int) { Composite<2, 3>::run(v); } };
-template <> struct Butterfly<9> { HD static void run(float2* v, const float2*, int) { Composite<3, 3>::run(v); } };
-template <> struct Butterfly<10> { HD static void run(float2* v, const float2*, int) { Composite<2, 5>::run(v); } };
-template <> struct Butterfly<12> { HD static void run(float2* v, const float2*, int) { Composite<4, 3>::run(v); } };
-template <> struct Butterfly<15> { HD static void run(float2* v, const float2*, int) { Composite<3, 5>::run(v); } };
-template <> struct Butterfly<16> { HD static void run(float2* v, const float2*, int) { Composite<4, 4>::run(v); } };
+// butterflies: fft_butterfly.cuh (generic over one complex value / the packed values of two rows)
 
 // One Stockham butterfly (index j of N/R) of a stage with sub-transform length Ns:  in -> out  (runtime plan / host)
 template <int R>
@@ -266,18 +135,66 @@ __device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m
 // =========================================================================================== compile-time plans
 // Real rows of even length N are transformed through ONE complex FFT of length H = N/2 each (z[n] = x[2n] + i x[2n+1], loaded
 // as one 4- or 8-byte word), followed by the split  X[m] = E[m] + W_N^m O[m],  E = (Z[m] + conj Z[H-m])/2,
-// O = (Z[m] - conj Z[H-m])/(2i).  A CTA owns ROWS = 8 consecutive latitude rows; the threads form GROUPS groups of TPG threads,
-// a group owns RPT = ROWS/GROUPS rows and one thread owns a butterfly index of those rows (twiddles and skewed indices are
-// computed once per index).
-template <int R0>
-__host__ __device__ constexpr int skew(int i) { return i + i / R0; }
+// O = (Z[m] - conj Z[H-m])/(2i).  A CTA owns ROWS consecutive latitude rows; the threads form GROUPS groups of TPG threads, a
+// group owns RPT = ROWS/GROUPS rows.  One thread carries the same butterfly index of TWO adjacent rows in the two halves of 64-bit
+// registers (value type cpair): every arithmetic instruction is a packed FADD2 / FMUL2 / FFMA2.  The FMA pipe does the same work
+// either way (FFMA2 issues at half the FFMA rate, measured with scripts/micro/f32x2.cu); what is halved is the number of issue
+// slots and of index computations.
+//
+// Exchange buffers (shared memory, Stockham: stage s reads one buffer and writes the other).  A buffer holds PROWS = ROWS/2 row
+// pairs as two planes of 8-byte elements (real parts of both rows / imaginary parts of both rows), so every access is an 8-byte
+// access by half warps and 16 lanes are conflict-free iff their slots are distinct modulo 16.  Element index -> slot:
+//   LaySkew   slot = i + i/16.  For the buffer the first stage writes (lane j stores elements j*R0 + r: stride R0, a power of two
+//             <= 16): 16 consecutive lanes land on 16 distinct slots mod 16, and runs of 16 consecutive elements that start at a
+//             multiple of 16 stay contiguous.
+//   LayBlock  slot = i + PAD * (i / BLK), BLK = R0*R1.  For the buffer the second stage writes (runs of Ns = R0 consecutive elements,
+//             one run per BLK): PAD spreads the runs of one half warp over distinct slots mod 16; consecutive elements inside a
+//             block stay contiguous (all loads of the following stage).
+// (scripts/smem_sim.py models the wavefronts of every access of a plan; the former single skew i + i/R0 cost 1.77x the ideal
+// wavefront count for the 1440-point plan, these two layouts 1.2x.)
+struct LaySkew {
+  __host__ __device__ static constexpr int at(int i) { return i + (i >> 4); }
+  __host__ __device__ static constexpr int size(int H) { return H + (H >> 4) + 1; }
+};
+template <int BLK, int PAD>
+struct LayBlock {
+  __host__ __device__ static constexpr int at(int i) { return i + PAD * (i / BLK); }
+  __host__ __device__ static constexpr int size(int H) { return H + PAD * ((H + BLK - 1) / BLK); }
+};
+__host__ __device__ constexpr int ct_block_pad(int R0, int R1) {
+  if (R0 >= 16) return 0;
+  int p = 0;
+  while ((R0 * R1 + p) % 16 != R0 % 16) ++p;
+  return p;
+}
 
-template <int H, int R0>
-__host__ __device__ constexpr int ct_bufstride() { return (skew<R0>(H) + 2) | 1; }  // odd stride: rows land on different banks
+// view of (some rows of) one exchange buffer
+template <int PLANE, class LAY>
+struct PairBuf {
+  typedef LAY layout;
+  pr* p;
+  __device__ __forceinline__ PairBuf operator+(int i) const { return PairBuf{p + i}; }
+  __device__ __forceinline__ cpair ld(int slot) const { cpair r; r.x = p[slot]; r.y = p[slot + PLANE]; return r; }
+  __device__ __forceinline__ void st(int slot, const cpair& v) const { p[slot] = v.x; p[slot + PLANE] = v.y; }
+};
 
-// stage of a compile-time plan: smem (skewed) -> smem (skewed), rows row0 .. row0 + RPT - 1
-template <int H, int R, int Ns, int R0, int TPG, int RPT>
-__device__ __forceinline__ void ct_stage(const float2* in, float2* out, const float2* tws /* [R][Ns]: W^(r k H/(Ns R)) */, int bufstride, int t, int row0) {
+// geometry shared by the kernels and the launcher
+template <int ROWS, int R0, int R1, int R2>
+struct CtGeom {
+  static constexpr int H = R0 * R1 * R2, PROWS = ROWS / 2;
+  typedef LaySkew LayS;
+  typedef LayBlock<R0 * R1, ct_block_pad(R0, R1)> LayB;
+  static constexpr int BSS = LayS::size(H), BSB = LayB::size(H);           // row-pair strides (8-byte elements)
+  static constexpr int PLANE_S = PROWS * BSS, PLANE_B = PROWS * BSB;
+  static constexpr int TW = (R1 * R0 + (R2 > 1 ? R2 * R0 * R1 : 0) + 1) & ~1;   // stage twiddles (float2), even count
+  static constexpr size_t smem_fixed = 8 * ((size_t)TW + 2 * PLANE_S + 2 * PLANE_B);
+  typedef PairBuf<PLANE_S, LayS> BufS;
+  typedef PairBuf<PLANE_B, LayB> BufB;
+};
+
+// stage of a compile-time plan: buffer `in` -> buffer `out`, row pairs row0 .. row0 + NPT - 1 of this thread's group
+template <class PI, class PO, int H, int R, int Ns, int TPG, int NPT>
+__device__ __forceinline__ void ct_stage(PI in, PO out, const float2* tws /* [R][Ns]: W^(r k H/(Ns R)) */, int in_stride, int out_stride, int t, int row0) {
   constexpr int NB = H / R;
   for (int j = t; j < NB; j += TPG) {
     const int k = j % Ns;
@@ -286,24 +203,24 @@ __device__ __forceinline__ void ct_stage(const float2* in, float2* out, const fl
     int si[R], di[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      si[r] = skew<R0>(j + r * NB);
-      di[r] = skew<R0>(j0 + r * Ns);
+      si[r] = PI::layout::at(j + r * NB);
+      di[r] = PO::layout::at(j0 + r * Ns);
       if (Ns > 1 && r > 0) w[r] = tws[r * Ns + k];   // consecutive threads -> consecutive k: conflict-free
     }
 #pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-      const float2* src = in + (row0 + q) * bufstride;
-      float2* dst = out + (row0 + q) * bufstride;
-      float2 v[R];
+    for (int q = 0; q < NPT; ++q) {
+      const PI src = in + (row0 + q) * in_stride;
+      const PO dst = out + (row0 + q) * out_stride;
+      cpair v[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float2 a = src[si[r]];
-        if (Ns > 1 && r > 0) a = cmul(a, w[r]);
+        cpair a = src.ld(si[r]);
+        if (Ns > 1 && r > 0) a = cmulw(a, w[r]);
         v[r] = a;
       }
       Butterfly<R>::run(v, nullptr, H);
 #pragma unroll
-      for (int r = 0; r < R; ++r) dst[di[r]] = v[r];
+      for (int r = 0; r < R; ++r) dst.st(di[r], v[r]);
     }
   }
 }
@@ -323,14 +240,7 @@ __device__ __forceinline__ void ct_build_twiddles(float2* tw1, float2* tw2, cons
       tw2[i] = twN[2 * (r * k)];
     }
 }
-template <int R0, int R1, int R2>
-__host__ __device__ constexpr int ct_tw_elems() { return R1 * R0 + (R2 > 1 ? R2 * R0 * R1 : 0); }
 
-__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* p) {
-  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
-  return make_float2(__bfloat162float(v.x), __bfloat162float(v.y));
-}
 __device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st_pair(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
@@ -351,31 +261,51 @@ template <> struct RawPair<__nv_bfloat16> {
   __device__ __forceinline__ float2 get() const { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 };
 
+__device__ __forceinline__ cpair pack_rows(float2 a, float2 b) { return mk<cpair>(make_pr(a.x, b.x), make_pr(a.y, b.y)); }
+
+// walk of the persistent CTA over the tiles (k tile, image r) without a division per tile
+struct TileWalk {
+  int kt, r, step_k, step_r, ntx;
+  __device__ __forceinline__ TileWalk(int ntx_) : ntx(ntx_) {
+    kt = blockIdx.x % ntx; r = blockIdx.x / ntx;
+    step_k = gridDim.x % ntx; step_r = gridDim.x / ntx;
+  }
+  __device__ __forceinline__ void next() {
+    kt += step_k; r += step_r;
+    if (kt >= ntx) { kt -= ntx; ++r; }
+  }
+};
+
 // x [R][nlat][nlon] -> latspec [mmax][2][R][kp]        plan (R0, R1, R2) for H = nlon / 2, R2 == 1 for two stages.
 // Persistent CTAs walk the (row group, image) tiles; the stage-0 operands of the NEXT tile are loaded into registers right after
 // stage 0 of the current one, so the HBM latency is hidden behind stages 1, 2 and the store pass.
 template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
 __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(const T* __restrict__ x, float* __restrict__ X, const FftParams prm) {
-  constexpr int H = R0 * R1 * R2, N = 2 * H;
-  constexpr int BS = ct_bufstride<H, R0>();
-  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
+  typedef CtGeom<ROWS, R0, R1, R2> G;
+  typedef typename G::BufS BufS;
+  typedef typename G::BufB BufB;
+  constexpr int H = G::H, N = 2 * H;
+  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS, PPT = RPT / 2;
   constexpr int NB0 = H / R0;
-  static_assert(ROWS % GROUPS == 0 && ROWS % 4 == 0, "row grouping");
+  constexpr int QUADS = ROWS / 4;
+  static_assert(ROWS % GROUPS == 0 && RPT % 2 == 0 && ROWS % 4 == 0, "row grouping");
   static_assert(NB0 <= TPG, "one stage-0 butterfly index per thread (register prefetch)");
+  static_assert(THREADS % (16 * QUADS) == 0, "split pass: 16 consecutive orders of one quad per half warp");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
   float2* tw2 = tw1 + R1 * R0;
-  float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
-  float2* b1 = b0 + ROWS * BS;
+  const BufS bS{reinterpret_cast<pr*>(tw1 + G::TW)};     // written by stage 0 (and stage 2)
+  const BufB bB{bS.p + 2 * G::PLANE_S};                  // written by stage 1
+  float2* twm = reinterpret_cast<float2*>(bB.p + 2 * G::PLANE_B);   // W_N^m, m < mmax (split pass)
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
-  const int row0 = grp * RPT;
+  const int row0 = grp * RPT, prow0 = grp * PPT;
   const int ntx = (prm.kp + ROWS - 1) / ROWS;
-  const int ntiles = ntx * prm.R;
   ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
+  for (int i = threadIdx.x; i < prm.mmax; i += THREADS) twm[i] = prm.twiddle[i];
 
   RawPair<T> raw[RPT][R0];
-  auto load_tile = [&](int tile) {
-    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
+  auto load_tile = [&](int kt, int r) {
+    const int k0 = kt * ROWS;
     const T* base = x + ((size_t)r * prm.nlat + k0) * N;
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
@@ -389,117 +319,137 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
       }
     }
   };
-  int tile = blockIdx.x;
-  if (tile < ntiles) load_tile(tile);
+  TileWalk tw(ntx);
+  if (tw.r < prm.R) load_tile(tw.kt, tw.r);
   __syncthreads();   // twiddle tables
 
-  for (; tile < ntiles; tile += gridDim.x) {
-    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
+  // split pass ownership: a half warp = 16 consecutive orders m of one quad of rows (conflict-free 8-byte shared loads)
+  const int qd = (threadIdx.x / 16) % QUADS;
+  const int m_first = (threadIdx.x % 16) + 16 * (threadIdx.x / (16 * QUADS));
+  const size_t mstride = (size_t)2 * prm.R * prm.kp, pstride = (size_t)prm.R * prm.kp;
+  const bool rnd = prm.round_tf32 != 0;
+
+  while (tw.r < prm.R) {
+    const int k0 = tw.kt * ROWS, r = tw.r;
+    const int kq = k0 + qd * 4;
+    // quadrature weights of this thread's quad of rows (consumed by the split pass at the end of the tile; zero in the padding)
+    float4 rs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prm.scale_mode == 0 && kq < prm.kp) rs4 = __ldg(reinterpret_cast<const float4*>(prm.rowscale + kq));
     // ---- stage 0 from the prefetched registers
     if (t < NB0) {
       int di[R0];
 #pragma unroll
-      for (int rr = 0; rr < R0; ++rr) di[rr] = skew<R0>(t * R0 + rr);
+      for (int rr = 0; rr < R0; ++rr) di[rr] = G::LayS::at(t * R0 + rr);
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-        float2 v[R0];
+      for (int p = 0; p < PPT; ++p) {
+        cpair v[R0];
 #pragma unroll
-        for (int rr = 0; rr < R0; ++rr) v[rr] = raw[q][rr].get();
+        for (int rr = 0; rr < R0; ++rr) v[rr] = pack_rows(raw[2 * p][rr].get(), raw[2 * p + 1][rr].get());
         Butterfly<R0>::run(v, nullptr, H);
-        float2* dst = b0 + (row0 + q) * BS;
+        const BufS dst = bS + (prow0 + p) * G::BSS;
 #pragma unroll
-        for (int rr = 0; rr < R0; ++rr) dst[di[rr]] = v[rr];
+        for (int rr = 0; rr < R0; ++rr) dst.st(di[rr], v[rr]);
       }
     }
-    if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);   // in flight until the next iteration
+    tw.next();
+    if (tw.r < prm.R) load_tile(tw.kt, tw.r);   // in flight until the next iteration
     __syncthreads();
-    ct_stage<H, R1, R0, R0, TPG, RPT>(b0, b1, tw1, BS, t, row0);
+    ct_stage<BufS, BufB, H, R1, R0, TPG, PPT>(bS, bB, tw1, G::BSS, G::BSB, t, prow0);
     __syncthreads();
-    const float2* res = b1;
     if (R2 > 1) {
-      ct_stage<H, (R2 > 1 ? R2 : 2), R0 * R1, R0, TPG, RPT>(b1, b0, tw2, BS, t, row0);
+      ct_stage<BufB, BufS, H, (R2 > 1 ? R2 : 2), R0 * R1, TPG, PPT>(bB, bS, tw2, G::BSB, G::BSS, t, prow0);
       __syncthreads();
-      res = b0;
     }
-    // ---- split + truncate + scale + store: a thread owns one quad of 4 rows and walks the orders m; two 16-byte stores per (m, quad)
-    {
-      constexpr int QUADS = ROWS / 4;
-      static_assert(THREADS % QUADS == 0, "quad ownership");
-      const int qd = threadIdx.x % QUADS;
-      float rsc[4];   // per-row factor: quadrature weight (SHT forward) or 1 (adjoint of irfft), 0 in the latitude padding
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + qd * 4 + i;
-        rsc[i] = (k < prm.nlat) ? (prm.scale_mode == 0 ? prm.rowscale[k] : 1.f) : 0.f;
+    // ---- split + truncate + scale + store: X[m] = (Z[m] + conj Z[H-m]) / 2 + W_N^m (Z[m] - conj Z[H-m]) / (2i), two 16-byte stores
+    auto split = [&](auto res, int stride) {
+      typedef typename decltype(res)::layout L;
+      pr rsc[2];   // per-row factor / 2: quadrature weight (SHT forward) or 1 (adjoint of irfft), 0 in the latitude padding
+      if (prm.scale_mode == 0) {
+        rsc[0] = make_pr(0.5f * rs4.x, 0.5f * rs4.y);
+        rsc[1] = make_pr(0.5f * rs4.z, 0.5f * rs4.w);
+      } else {
+        rsc[0] = make_pr(kq + 0 < prm.nlat ? 0.5f : 0.f, kq + 1 < prm.nlat ? 0.5f : 0.f);
+        rsc[1] = make_pr(kq + 2 < prm.nlat ? 0.5f : 0.f, kq + 3 < prm.nlat ? 0.5f : 0.f);
       }
-      const float2* rb = res + (qd * 4) * BS;
-      const int kq = k0 + qd * 4;
+      const auto rb = res + (qd * 2) * stride;
       float* xbase = X + (size_t)r * prm.kp + kq;
-      const size_t mstride = (size_t)2 * prm.R * prm.kp, pstride = (size_t)prm.R * prm.kp;
-      const bool rnd = prm.round_tf32 != 0;
-      for (int m = threadIdx.x / QUADS; m < prm.mmax; m += THREADS / QUADS) {
-        const float2 wm = __ldg(prm.twiddle + m);                 // W_N^m
-        const int im = skew<R0>(m == H ? 0 : m), ic = skew<R0>((m == 0 || m == H) ? 0 : H - m);
+      for (int m = m_first; m < prm.mmax; m += THREADS / QUADS) {
+        const float2 wm = twm[m];                                 // W_N^m
+        const int im = L::at(m == H ? 0 : m), ic = L::at((m == 0 || m == H) ? 0 : H - m);
         const float msc = (prm.scale_mode == 1 && !(m == 0 || 2 * m == N)) ? 2.f : 1.f;
-        float re[4], imv[4];
+        pr re[2], imv[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 Z = rb[i * BS + im], Zc = rb[i * BS + ic];
-          const float2 E = make_float2(0.5f * (Z.x + Zc.x), 0.5f * (Z.y - Zc.y));
-          const float2 Od = make_float2(0.5f * (Z.y + Zc.y), -0.5f * (Z.x - Zc.x));   // (Z - conj Zc) / (2i)
-          const float2 WO = cmul(wm, Od);
-          const float sc = rsc[i] * msc;
-          const float a = (E.x + WO.x) * sc, b = (E.y + WO.y) * sc;
-          re[i] = rnd ? tf32_rn(a) : a;
-          imv[i] = rnd ? tf32_rn(b) : b;
+        for (int i = 0; i < 2; ++i) {
+          const cpair Z = rb.ld(i * stride + im), Zc = rb.ld(i * stride + ic);
+          const pr ex = Z.x + Zc.x, ey = Z.y - Zc.y;                            // 2 E
+          const cpair od = mk<cpair>(Z.y + Zc.y, Zc.x - Z.x);                    // 2 O = (Z - conj Zc) / i
+          const cpair wo = cmulw(od, wm);
+          const pr sc = rmul(rsc[i], msc);
+          re[i] = (ex + wo.x) * sc;
+          imv[i] = (ey + wo.y) * sc;
+        }
+        float4 o_re = make_float4(re[0].v.x, re[0].v.y, re[1].v.x, re[1].v.y);
+        float4 o_im = make_float4(imv[0].v.x, imv[0].v.y, imv[1].v.x, imv[1].v.y);
+        if (rnd) {
+          o_re = make_float4(tf32_rn(o_re.x), tf32_rn(o_re.y), tf32_rn(o_re.z), tf32_rn(o_re.w));
+          o_im = make_float4(tf32_rn(o_im.x), tf32_rn(o_im.y), tf32_rn(o_im.z), tf32_rn(o_im.w));
         }
         if (kq < prm.kp) {
           float* dst = xbase + (size_t)m * mstride;
-          *reinterpret_cast<float4*>(dst) = make_float4(re[0], re[1], re[2], re[3]);
-          *reinterpret_cast<float4*>(dst + pstride) = make_float4(imv[0], imv[1], imv[2], imv[3]);
+          *reinterpret_cast<float4*>(dst) = o_re;
+          *reinterpret_cast<float4*>(dst + pstride) = o_im;
         }
       }
-    }
-    __syncthreads();   // b0 / b1 are reused by the next tile
+    };
+    if constexpr (R2 > 1) split(bS, G::BSS);
+    else split(bB, G::BSB);
+    __syncthreads();   // the buffers are reused by the next tile
   }
 }
 
 // latspec [mmax][2][R][kp] -> y [R][nlat][nlon]   (persistent, with register prefetch of the next tile's spectrum)
 template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
 __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
-  constexpr int H = R0 * R1 * R2, N = 2 * H;
-  constexpr int BS = ct_bufstride<H, R0>();
-  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS;
+  typedef CtGeom<ROWS, R0, R1, R2> G;
+  typedef typename G::BufS BufS;
+  typedef typename G::BufB BufB;
+  constexpr int H = G::H, N = 2 * H;
+  constexpr int THREADS = GROUPS * TPG, RPT = ROWS / GROUPS, PPT = RPT / 2;
   constexpr int RL = (R2 > 1) ? R2 : R1;       // radix of the last stage (fused with the store)
   constexpr int NsL = H / RL;
   constexpr int QUADS = ROWS / 4;
-  constexpr int NITEMS = (H / 2 + 1) * QUADS;
-  constexpr int IPT = (NITEMS + THREADS - 1) / THREADS;   // spectrum-build items per thread
+  constexpr int NQ16 = (H / 2 + 1 + 15) / 16;              // groups of 16 spectrum indices q in [0, H/2]
+  constexpr int NITEMS = NQ16 * 16 * QUADS;                // item = (q, quad of 4 rows)
+  constexpr int IPT = (NITEMS + THREADS - 1) / THREADS;    // spectrum-build items per thread
+  static_assert(RPT % 2 == 0 && ROWS % 4 == 0, "row grouping");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw1 = reinterpret_cast<float2*>(smem_raw);
   float2* tw2 = tw1 + R1 * R0;
-  float2* b0 = tw1 + ct_tw_elems<R0, R1, R2>();
-  float2* b1 = b0 + ROWS * BS;
+  const BufS bS{reinterpret_cast<pr*>(tw1 + G::TW)};     // written by stage 0 (stride-R0 stores)
+  const BufB bB{bS.p + 2 * G::PLANE_S};                  // written by the spectrum build and by stage 1
+  float2* twm = reinterpret_cast<float2*>(bB.p + 2 * G::PLANE_B);   // W_N^q, q < mmax (spectrum build)
   const int grp = threadIdx.x / TPG, t = threadIdx.x - grp * TPG;
-  const int row0 = grp * RPT;
+  const int row0 = grp * RPT, prow0 = grp * PPT;
   const int mmax = prm.mmax;
   const int ntx = (prm.kp + ROWS - 1) / ROWS;
-  const int ntiles = ntx * prm.R;
   ct_build_twiddles<R0, R1, R2>(tw1, tw2, prm.twiddle, THREADS);
+  for (int i = threadIdx.x; i < prm.mmax; i += THREADS) twm[i] = prm.twiddle[i];
   const float2* twL = (R2 > 1) ? tw2 : tw1;   // table of the last stage: [RL][NsL]
 
-  // item = (q in [0, H/2], quad of 4 rows): X[q] and X[H-q] of 4 rows (re, im) = four 16-byte loads
+  // item e -> (q, quad): a half warp owns 16 consecutive q of one quad.  X[q] and X[H-q] of 4 rows (re, im) = four 16-byte loads
   float4 pa_r[IPT], pa_i[IPT], pb_r[IPT], pb_i[IPT];
-  auto load_tile = [&](int tile) {
-    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
+  auto item_q = [](int e) { return (e % 16) + 16 * (e / (16 * QUADS)); };
+  auto item_quad = [](int e) { return (e / 16) % QUADS; };
+  auto load_tile = [&](int kt, int r) {
+    const int k0 = kt * ROWS;
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
       const int e = threadIdx.x + it * THREADS;
-      const int qd = e % QUADS, q = e / QUADS, q2 = H - q;
+      const int qd = item_quad(e), q = item_q(e), q2 = H - q;
       const int k = k0 + qd * 4;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       pa_r[it] = z; pa_i[it] = z; pb_r[it] = z; pb_i[it] = z;
-      if (e < NITEMS && k < prm.kp) {
+      if (e < NITEMS && q <= H / 2 && k < prm.kp) {
         if (q < mmax) {
           const float* src = Zs + (((size_t)q * 2) * prm.R + r) * prm.kp + k;
           pa_r[it] = __ldg(reinterpret_cast<const float4*>(src));
@@ -513,91 +463,110 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(co
       }
     }
   };
-  int tile = blockIdx.x;
-  if (tile < ntiles) load_tile(tile);
+  TileWalk tw(ntx);
+  if (tw.r < prm.R) load_tile(tw.kt, tw.r);
   __syncthreads();
 
-  for (; tile < ntiles; tile += gridDim.x) {
-    const int k0 = (tile % ntx) * ROWS, r = tile / ntx;
-    // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re)
+  while (tw.r < prm.R) {
+    const int k0 = tw.kt * ROWS, r = tw.r;
+    // per-row output factors of this thread's rows and the channel bias (consumed by the fused store at the end of the tile)
+    float rsv[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) rsv[i] = (prm.scale_mode == 1 && k0 + row0 + i < prm.nlat) ? __ldg(prm.rowscale + k0 + row0 + i) : 1.f;
+    const float bias = prm.bias ? __ldg(prm.bias + r % prm.C) : 0.f;
+    // ---- build Z'[q] = (X[q] + conj X[H-q]) + i (X[q] - conj X[H-q]) W_N^-q for q in [0, H), stored swapped (im, re).
+    //      With A = X[q], B = X[H-q]:  Z'[q] = s + i d conj(w),  Z'[H-q] = conj(s) + i conj(d) w  (W_N^(H-q) = -conj W_N^q).
+    //      Rows beyond nlat carry whatever the padding holds; they are never stored.
 #pragma unroll
     for (int it = 0; it < IPT; ++it) {
       const int e = threadIdx.x + it * THREADS;
-      if (e >= NITEMS) continue;
-      const int qd = e % QUADS, q = e / QUADS;
+      const int qd = item_quad(e), q = item_q(e);
+      if (e >= NITEMS || q > H / 2) continue;
       const int q2 = H - q;                                    // partner index (q2 == H for q == 0)
-      const int k = k0 + qd * 4;
-      const float ar[4] = {pa_r[it].x, pa_r[it].y, pa_r[it].z, pa_r[it].w}, ai[4] = {pa_i[it].x, pa_i[it].y, pa_i[it].z, pa_i[it].w};
-      const float br[4] = {pb_r[it].x, pb_r[it].y, pb_r[it].z, pb_r[it].w}, bi[4] = {pb_i[it].x, pb_i[it].y, pb_i[it].z, pb_i[it].w};
+      const int s1 = G::LayB::at(q), s2 = G::LayB::at(q2 == H ? 0 : q2);
+      if (q >= mmax) {   // X[q] = X[H-q] = 0 (truncated spectrum): Z'[q] = Z'[H-q] = 0
+        const cpair zero = mk<cpair>(make_pr(0.f, 0.f), make_pr(0.f, 0.f));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const BufB rowp = bB + (qd * 2 + i) * G::BSB;
+          rowp.st(s1, zero);
+          if (q2 != q) rowp.st(s2, zero);
+        }
+        continue;
+      }
       const bool a_self = (q == 0), b_self = (q2 == H);        // DC and Nyquist: imaginary part ignored, no halving
       const float ha = (prm.scale_mode == 1 && !a_self) ? 0.5f : 1.f;
       const float hb = (prm.scale_mode == 1 && !b_self) ? 0.5f : 1.f;
-      const float2 wq = __ldg(prm.twiddle + q);                 // W_N^q ; W_N^-q = conj
-      const float2 wq2 = __ldg(prm.twiddle + q2);               // q2 <= H < N
+      const float2 wq = twm[q];                                 // W_N^q
+      const float ar[4] = {pa_r[it].x, pa_r[it].y, pa_r[it].z, pa_r[it].w}, ai[4] = {pa_i[it].x, pa_i[it].y, pa_i[it].z, pa_i[it].w};
+      const float br[4] = {pb_r[it].x, pb_r[it].y, pb_r[it].z, pb_r[it].w}, bi[4] = {pb_i[it].x, pb_i[it].y, pb_i[it].z, pb_i[it].w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = qd * 4 + i;
-        const bool valid = (k + i) < prm.nlat;
-        const float Ar = valid ? ar[i] * ha : 0.f, Ai = (valid && !a_self) ? ai[i] * ha : 0.f;   // A = X[q]
-        const float Br = valid ? br[i] * hb : 0.f, Bi = (valid && !b_self) ? bi[i] * hb : 0.f;   // B = X[H-q]
-        {
-          const float sr = Ar + Br, si2 = Ai - Bi;              // A + conj B
-          const float dr = Ar - Br, dii = Ai + Bi;              // A - conj B
-          const float tr = dr * wq.x + dii * wq.y, ti = dii * wq.x - dr * wq.y;   // (A - conj B) * conj(wq)
-          b0[row * BS + skew<R0>(q)] = make_float2(si2 + tr, sr - ti);            // Z'[q] = s + i t, stored (im, re)
-        }
+      for (int i = 0; i < 2; ++i) {
+        pr Ar = make_pr(ar[2 * i], ar[2 * i + 1]), Ai = a_self ? make_pr(0.f, 0.f) : make_pr(ai[2 * i], ai[2 * i + 1]);
+        pr Br = make_pr(br[2 * i], br[2 * i + 1]), Bi = b_self ? make_pr(0.f, 0.f) : make_pr(bi[2 * i], bi[2 * i + 1]);
+        if (prm.scale_mode == 1) { Ar = rmul(Ar, ha); Ai = rmul(Ai, ha); Br = rmul(Br, hb); Bi = rmul(Bi, hb); }
+        const pr sr = Ar + Br, si = Ai - Bi;              // s = A + conj B
+        const pr dr = Ar - Br, di = Ai + Bi;              // d = A - conj B
+        const BufB rowp = bB + (qd * 2 + i) * G::BSB;
+        // t = d conj(w) = (dr wx + di wy, di wx - dr wy);  Z'[q] = (sr - t.y, si + t.x), stored (im, re)
+        rowp.st(s1, mk<cpair>(rfma(di, wq.y, rfma(dr, wq.x, si)), rfma(dr, wq.y, rfma(di, -wq.x, sr))));
         if (q != 0 && q2 != q) {
-          const float sr = Br + Ar, si2 = Bi - Ai;
-          const float dr = Br - Ar, dii = Bi + Ai;
-          const float tr = dr * wq2.x + dii * wq2.y, ti = dii * wq2.x - dr * wq2.y;
-          b0[row * BS + skew<R0>(q2)] = make_float2(si2 + tr, sr - ti);
+          // conj(d) w = (dr wx + di wy, dr wy - di wx);  Z'[H-q] = (sr - (dr wy - di wx), -si + (dr wx + di wy)), stored (im, re)
+          const pr nsi = Bi - Ai;
+          rowp.st(s2, mk<cpair>(rfma(di, wq.y, rfma(dr, wq.x, nsi)), rfma(dr, -wq.y, rfma(di, wq.x, sr))));
         }
       }
     }
-    if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);   // in flight until the next iteration
+    tw.next();
+    if (tw.r < prm.R) load_tile(tw.kt, tw.r);   // in flight until the next iteration
     __syncthreads();
-    ct_stage<H, R0, 1, R0, TPG, RPT>(b0, b1, nullptr, BS, t, row0);
+    ct_stage<BufB, BufS, H, R0, 1, TPG, PPT>(bB, bS, nullptr, G::BSB, G::BSS, t, prow0);
     __syncthreads();
-    const float2* src = b1;
     if (R2 > 1) {
-      ct_stage<H, R1, R0, R0, TPG, RPT>(b1, b0, tw1, BS, t, row0);
+      ct_stage<BufS, BufB, H, R1, R0, TPG, PPT>(bS, bB, tw1, G::BSS, G::BSB, t, prow0);
       __syncthreads();
-      src = b0;
     }
     // ---- last stage fused with the store: butterfly j yields z[e], e = j + rr * NsL, (x[2e], x[2e+1]) = (Im, Re) of the swapped result
-    {
+    auto last = [&](auto src, int stride) {
+      typedef typename decltype(src)::layout L;
       T* base = y + ((size_t)r * prm.nlat + k0) * N;
-      const float bias = prm.bias ? prm.bias[r % prm.C] : 0.f;
+      const pr bias2 = make_pr(bias, bias);
       for (int j = t; j < NsL; j += TPG) {
         float2 w[RL];
         int si[RL];
 #pragma unroll
         for (int rr = 0; rr < RL; ++rr) {
-          si[rr] = skew<R0>(j + rr * NsL);
+          si[rr] = L::at(j + rr * NsL);
           if (rr > 0) w[rr] = twL[rr * NsL + j];   // k = j
         }
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-          const int row = row0 + q;
-          const float2* sp = src + row * BS;
-          float2 v[RL];
+        for (int p = 0; p < PPT; ++p) {
+          const int rowa = row0 + 2 * p, rowb = rowa + 1;
+          const auto sp = src + (prow0 + p) * stride;
+          cpair v[RL];
 #pragma unroll
           for (int rr = 0; rr < RL; ++rr) {
-            float2 a = sp[si[rr]];
-            if (rr > 0) a = cmul(a, w[rr]);
+            cpair a = sp.ld(si[rr]);
+            if (rr > 0) a = cmulw(a, w[rr]);
             v[rr] = a;
           }
           Butterfly<RL>::run(v, nullptr, H);
-          if (k0 + row < prm.nlat) {
-            const float sc = (prm.scale_mode == 1) ? prm.rowscale[k0 + row] : 1.f;
-            T* rp = base + (size_t)row * N + 2 * j;
+          const bool va = (k0 + rowa) < prm.nlat, vb = (k0 + rowb) < prm.nlat;
+          const pr sc = make_pr(rsv[2 * p], rsv[2 * p + 1]);
+          T* rpa = base + (size_t)rowa * N + 2 * j;
+          T* rpb = rpa + N;
 #pragma unroll
-            for (int rr = 0; rr < RL; ++rr) st_pair(rp + 2 * rr * NsL, v[rr].y * sc + bias, v[rr].x * sc + bias);
+          for (int rr = 0; rr < RL; ++rr) {
+            const pr o0 = rfma(v[rr].y, sc, bias2), o1 = rfma(v[rr].x, sc, bias2);
+            if (va) st_pair(rpa + 2 * rr * NsL, o0.v.x, o1.v.x);
+            if (vb) st_pair(rpb + 2 * rr * NsL, o0.v.y, o1.v.y);
           }
         }
       }
-    }
-    __syncthreads();   // b0 / b1 are reused by the next tile
+    };
+    if constexpr (R2 > 1) last(bB, G::BSB);
+    else last(bS, G::BSS);
+    __syncthreads();   // the buffers are reused by the next tile
   }
 }
 
@@ -752,9 +721,9 @@ static FftParams make_params(const Plan* pl, int B, int C, int scale_mode, const
 
 template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
 static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const FftParams& prm, cudaStream_t st) {
-  constexpr int H = R0 * R1 * R2;
-  constexpr size_t smem = sizeof(float2) * ((size_t)ct_tw_elems<R0, R1, R2>() + 2 * ROWS * ct_bufstride<H, R0>());
-  static_assert(smem <= 227 * 1024, "plan does not fit in shared memory");
+  typedef CtGeom<ROWS, R0, R1, R2> G;
+  static_assert(G::smem_fixed + 8 * (G::H + 2) <= 227 * 1024, "plan does not fit in shared memory");
+  const size_t smem = G::smem_fixed + sizeof(float2) * (size_t)((pl->mmax + 1) & ~1);   // + W_N^m, m < mmax
   // persistent CTAs: as many as fit concurrently (by shared memory), each walks tiles blockIdx.x, + gridDim.x, ...
   const int ntiles = ceil_div(pl->kp, ROWS) * prm.R;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -763,11 +732,13 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   dim3 grid(ntiles < per_sm * sms ? ntiles : per_sm * sms);
   if (dir == 0) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
+    auto k = fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
   } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB><<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
+    auto k = fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
   }
   B200_CHECK_LAUNCH();
   return 0;
@@ -776,17 +747,17 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
 // lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
 // i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
 #define CT_PLANS(X)             \
-  X(8, 2, 96, 8, 10, 9, 2)      /* nlon 1440: 2 groups x 4 rows per thread (no spills at 2 CTAs/SM; measured faster than 4 x 2) */ \
+  X(4, 2, 96, 8, 10, 9, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM) */ \
   X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
   X(8, 4, 64, 8, 6, 5, 2)       /* nlon  480 */ \
   X(8, 4, 64, 4, 9, 5, 2)       /* nlon  360 */ \
   X(8, 4, 64, 8, 5, 3, 2)       /* nlon  240 */ \
   X(8, 4, 64, 2, 9, 5, 2)       /* nlon  180 */ \
   X(8, 4, 32, 8, 3, 3, 2)       /* nlon  144 */ \
-  X(8, 8, 32, 4, 4, 4, 2)       /* nlon  128 */ \
-  X(8, 8, 32, 4, 4, 3, 2)       /* nlon   96 */ \
-  X(8, 8, 32, 4, 3, 3, 2)       /* nlon   72 */ \
-  X(8, 8, 32, 4, 8, 1, 2)       /* nlon   64 */ \
+  X(8, 4, 32, 4, 4, 4, 2)       /* nlon  128 */ \
+  X(8, 4, 32, 4, 4, 3, 2)       /* nlon   96 */ \
+  X(8, 4, 32, 4, 3, 3, 2)       /* nlon   72 */ \
+  X(8, 4, 32, 4, 8, 1, 2)       /* nlon   64 */ \
   X(8, 4, 32, 8, 4, 4, 2)       /* nlon  256 */ \
   X(8, 4, 64, 8, 8, 4, 2)       /* nlon  512 */ \
   X(8, 4, 64, 8, 8, 8, 2)       /* nlon 1024 */ \
@@ -798,9 +769,9 @@ static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const
   // the compile-time plans move element pairs / quads with vector loads: both tensors must be 16-byte aligned
   if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return 0;
   *handled = true;
-  // experiment switch (B200SHT_FFT_VARIANT=1): 1440-point rows with 4 thread groups x 2 rows per thread
+  // A/B switch (B200SHT_FFT_VARIANT=1): 1440-point rows as 8-row tiles with 2 CTAs per SM instead of 4-row tiles with 3
   static const int variant = [] { const char* e = getenv("B200SHT_FFT_VARIANT"); return e ? atoi(e) : 0; }();
-  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 4, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
+  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
 #define X(RW, G, TP, A, B_, C_, MB) \
   if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_, MB>(pl, dir, in, out, prm, st);
   CT_PLANS(X)
