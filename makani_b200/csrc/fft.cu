@@ -150,8 +150,13 @@ __device__ __forceinline__ float mode_scale_analysis(const FftParams& prm, int m
 //   LayBlock  slot = i + PAD * (i / BLK), BLK = R0*R1.  For the buffer the second stage writes (runs of Ns = R0 consecutive elements,
 //             one run per BLK): PAD spreads the runs of one half warp over distinct slots mod 16; consecutive elements inside a
 //             block stay contiguous (all loads of the following stage).
+//   LayId     slot = i.  The last stage of the analysis writes runs of consecutive elements and the split pass reads runs (ascending
+//             m, descending H-m): the memory of the first buffer is reused with the identity layout for them.
 // (scripts/smem_sim.py models the wavefronts of every access of a plan; the former single skew i + i/R0 cost 1.77x the ideal
 // wavefront count for the 1440-point plan, these two layouts 1.2x.)
+struct LayId {
+  __host__ __device__ static constexpr int at(int i) { return i; }
+};
 struct LaySkew {
   __host__ __device__ static constexpr int at(int i) { return i + (i >> 4); }
   __host__ __device__ static constexpr int size(int H) { return H + (H >> 4) + 1; }
@@ -190,6 +195,7 @@ struct CtGeom {
   static constexpr size_t smem_fixed = 8 * ((size_t)TW + 2 * PLANE_S + 2 * PLANE_B);
   typedef PairBuf<PLANE_S, LayS> BufS;
   typedef PairBuf<PLANE_B, LayB> BufB;
+  typedef PairBuf<PLANE_S, LayId> BufI;   // the memory of BufS under the identity layout
 };
 
 // stage of a compile-time plan: buffer `in` -> buffer `out`, row pairs row0 .. row0 + NPT - 1 of this thread's group
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
     ct_stage<BufS, BufB, H, R1, R0, TPG, PPT>(bS, bB, tw1, G::BSS, G::BSB, t, prow0);
     __syncthreads();
     if (R2 > 1) {
-      ct_stage<BufB, BufS, H, (R2 > 1 ? R2 : 2), R0 * R1, TPG, PPT>(bB, bS, tw2, G::BSB, G::BSS, t, prow0);
+      ct_stage<BufB, typename G::BufI, H, (R2 > 1 ? R2 : 2), R0 * R1, TPG, PPT>(bB, typename G::BufI{bS.p}, tw2, G::BSB, G::BSS, t, prow0);
       __syncthreads();
     }
     // ---- split + truncate + scale + store: X[m] = (Z[m] + conj Z[H-m]) / 2 + W_N^m (Z[m] - conj Z[H-m]) / (2i), two 16-byte stores
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
         }
       }
     };
-    if constexpr (R2 > 1) split(bS, G::BSS);
+    if constexpr (R2 > 1) split(typename G::BufI{bS.p}, G::BSS);
     else split(bB, G::BSB);
     __syncthreads();   // the buffers are reused by the next tile
   }
@@ -747,7 +753,8 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
 // lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
 // i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
 #define CT_PLANS(X)             \
-  X(4, 2, 96, 8, 10, 9, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM) */ \
+  X(4, 2, 96, 8, 9, 10, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM);
+                                   radix order 8-9-10: every exchange access conflict-free in scripts/smem_sim.py (8-10-9: 1.17x / 1.11x) */ \
   X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
   X(8, 4, 64, 8, 6, 5, 2)       /* nlon  480 */ \
   X(8, 4, 64, 4, 9, 5, 2)       /* nlon  360 */ \
@@ -771,7 +778,8 @@ static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const
   *handled = true;
   // A/B switch (B200SHT_FFT_VARIANT=1): 1440-point rows as 8-row tiles with 2 CTAs per SM instead of 4-row tiles with 3
   static const int variant = [] { const char* e = getenv("B200SHT_FFT_VARIANT"); return e ? atoi(e) : 0; }();
-  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 10, 9, 2>(pl, dir, in, out, prm, st);
+  if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 9, 10, 2>(pl, dir, in, out, prm, st);
+  if (variant == 2 && pl->nlon == 1440) return launch_ct<T, 4, 2, 96, 8, 10, 9, 3>(pl, dir, in, out, prm, st);
 #define X(RW, G, TP, A, B_, C_, MB) \
   if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_, MB>(pl, dir, in, out, prm, st);
   CT_PLANS(X)
