@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Rank the source lines of a kernel by warp-stall samples from an `ncu --set full --import-source on` report.
 
-usage: python scripts/ncu_hot.py gpurun_out/prof_fft_analysis.ncu-rep [top_n]
+usage: python scripts/ncu_hot.py gpurun_out/prof_fft_analysis.ncu-rep [top_n] [kernel-name substring]
 Prints, per source line: samples, share, instructions executed, dominant stall reasons, shared-memory excess wavefronts.
 """
 import csv
@@ -13,9 +13,10 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    want = sys.argv[3] if len(sys.argv) > 3 else None
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, cur_file, lines = None, None, []
+    hdr, cur_file, lines, cur_fn, seen = None, None, [], "", set()
     for r in rows:
         if not r:
             continue
@@ -23,12 +24,17 @@ def main():
             cur_file = r[1].split("/")[-1]
             continue
         if r[0] == "Function Name":
-            print("kernel:", r[1][:160])
+            cur_fn = r[1]
+            if cur_fn not in seen and (want is None or want in cur_fn):
+                seen.add(cur_fn)
+                print("kernel:", cur_fn[:160])
             continue
         if r[0] == "Line No":
             hdr = r
             continue
         if hdr is None or len(r) < len(hdr) or r[2] != "-":   # keep the per-source-line aggregate rows only (Address == "-")
+            continue
+        if want is not None and want not in cur_fn:
             continue
         d = dict(zip(hdr, r))
         # the header has two "Source" columns; positional access for the first two
