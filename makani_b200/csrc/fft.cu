@@ -779,7 +779,6 @@ static int dispatch_ct(const Plan* pl, int dir, const void* in, void* out, const
   // A/B switch (B200SHT_FFT_VARIANT=1): 1440-point rows as 8-row tiles with 2 CTAs per SM instead of 4-row tiles with 3
   static const int variant = [] { const char* e = getenv("B200SHT_FFT_VARIANT"); return e ? atoi(e) : 0; }();
   if (variant == 1 && pl->nlon == 1440) return launch_ct<T, 8, 2, 96, 8, 9, 10, 2>(pl, dir, in, out, prm, st);
-  if (variant == 2 && pl->nlon == 1440) return launch_ct<T, 4, 2, 96, 8, 10, 9, 3>(pl, dir, in, out, prm, st);
 #define X(RW, G, TP, A, B_, C_, MB) \
   if (pl->nlon == 2 * (A) * (B_) * (C_)) return launch_ct<T, RW, G, TP, A, B_, C_, MB>(pl, dir, in, out, prm, st);
   CT_PLANS(X)
