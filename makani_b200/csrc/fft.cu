@@ -756,7 +756,7 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   X(4, 2, 96, 8, 9, 10, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM);
                                    radix order 8-9-10: every exchange access conflict-free in scripts/smem_sim.py (8-10-9: 1.17x / 1.11x) */ \
   X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
-  X(8, 4, 64, 8, 6, 5, 2)       /* nlon  480 */ \
+  X(8, 4, 64, 8, 5, 6, 2)       /* nlon  480 */ \
   X(8, 4, 64, 4, 9, 5, 2)       /* nlon  360 */ \
   X(8, 4, 64, 8, 5, 3, 2)       /* nlon  240 */ \
   X(8, 4, 64, 2, 9, 5, 2)       /* nlon  180 */ \

@@ -51,6 +51,7 @@ def main():
         "small": (64, 128, 64, 128, 32, 33, 2, 8),
         "odd": (91, 180, 181, 360, 91, 91, 1, 10),
         "sfno": (721, 1440, 240, 480, 240, 241, 1, 16),
+        "block73": (721, 1440, 721, 1440, 240, 241, 1, 73),   # the headline block of bench.py, one sample split over h x w ranks
     }
     ok_all = True
     out = {}

@@ -50,6 +50,9 @@ class Tally:
             i += b
         self.rows.append((name, w, i))
 
+    def total(self):
+        return sum(w for _, w, _ in self.rows), sum(i for _, _, i in self.rows)
+
     def report(self, title):
         print(title)
         tw = ti = 0
@@ -84,14 +87,14 @@ def stage_accesses(H, R, Ns, TPG, lay_in, lay_out):
     return loads, stores
 
 
-def main():
-    H, R0, R1, R2, TPG = (int(x) for x in sys.argv[1:6])
-    mmax = int(sys.argv[6]) if len(sys.argv) > 6 else H // 3 + 1
+def simulate(H, R0, R1, R2, TPG, mmax, verbose=True):
+    """-> {"analysis": (wavefronts, ideal), "synthesis": (wavefronts, ideal)}"""
     pad = block_pad(R0, R1)
     blk = R0 * R1
     skew = lambda i: i + (i >> 4)
     block = lambda i: i + pad * (i // blk)
-    print(f"H={H} plan {R0}x{R1}x{R2} TPG={TPG} mmax={mmax}  LayBlock pad={pad} per {blk}")
+    if verbose:
+        print(f"H={H} plan {R0}x{R1}x{R2} TPG={TPG} mmax={mmax}  LayBlock pad={pad} per {blk}")
 
     # ---- analysis: stage0 regs->S, stage1 S->B, stage2 B->S, split from S (3 stages) or B (2 stages)
     t = Tally()
@@ -120,7 +123,7 @@ def main():
                 slots.append(res(idx) + (lane // 16) * 100003 * 16)   # second half warp: another quad (different rows, own phase)
             instrs.append(slots)
     t.add("split loads", instrs)
-    t.report("analysis")
+    out = {"analysis": t.report("analysis") if verbose else t.total()}
 
     # ---- synthesis: build -> B, stage0 B->S, stage1 S->B, fused last stage loads from B (3 stages) or S (2 stages)
     t = Tally()
@@ -149,7 +152,14 @@ def main():
     else:
         ld, _ = stage_accesses(H, R1, R0, TPG, skew, None)
         t.add("last stage loads (LaySkew)", ld)
-    t.report("synthesis")
+    out["synthesis"] = t.report("synthesis") if verbose else t.total()
+    return out
+
+
+def main():
+    H, R0, R1, R2, TPG = (int(x) for x in sys.argv[1:6])
+    mmax = int(sys.argv[6]) if len(sys.argv) > 6 else H // 3 + 1
+    simulate(H, R0, R1, R2, TPG, mmax)
 
 
 if __name__ == "__main__":
