@@ -2,17 +2,16 @@
 // InverseRealSHT; reference call sites /root/reference/makani/models/common/spectral_convolution.py:239,253 and
 // the FFT twin /root/reference/makani/mpu/fft.py:62,109).
 //
-// One CTA transforms KC = 2*PAIRS consecutive latitude rows of one (batch, channel) image: two real rows are packed
-// into one complex sequence, transformed with a mixed-radix Stockham FFT (radices up to 16 kept in registers, shared
-// memory only for the exchange between stages), split back into the two half spectra, truncated to mmax, scaled and
-// written in the "latspec" layout [m][re/im][row r][k] so that the KC results of one (m, re/im) form one contiguous
-// 32-byte sector and the Legendre GEMM reads K-major operands straight from it.
+// A CTA transforms a tile of consecutive latitude rows of one (batch, channel) image with a mixed-radix Stockham FFT (radices up to
+// 16 kept in registers, shared memory only for the exchange between stages), truncates to mmax, scales and writes the "latspec"
+// layout [m][re/im][row r][k]: the results of one tile for one (m, re/im) are one contiguous 16- or 32-byte piece and the Legendre
+// GEMM reads K-major operands straight from it.
 //
-// Two kernel families share the butterflies:
-//   *_ct  : radix plan fixed at compile time (lengths 64 ... 2880 listed in CT_PLANS): all index arithmetic folds to
-//           constants, first stage fused with the global load, last stage of the inverse fused with the store,
-//           shared-memory indices skewed by i / R0 to spread the stride-R0 writes of the first stage over the banks.
-//   *_rt  : any length whose prime factors are <= 13 (runtime plan).
+// Two kernel families share the butterflies (fft_butterfly.cuh):
+//   *_ct  : radix plan fixed at compile time (CT_PLANS): one half-length complex FFT per real row, two rows per 64-bit register
+//           pair (packed FADD2/FMUL2/FFMA2), persistent CTAs with register prefetch of the next tile, first stage fused with the
+//           global load, last stage of the inverse fused with the store, per-buffer conflict-free shared-memory layouts.
+//   *_rt  : any length whose prime factors are <= 13 (runtime plan), two real rows packed into one complex sequence.
 //
 // The stage / butterfly code is __host__ __device__ so that the same arithmetic is unit-tested on the CPU
 // (b200sht_debug_fft_host) without a GPU.
@@ -750,8 +749,8 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   return 0;
 }
 
-// lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two (the skew
-// i + i/R0 is a shift); TPG ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
+// lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2, CTAs/SM) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two <= 16
+// (LaySkew); TPG >= H/R0, ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
 #define CT_PLANS(X)             \
   X(4, 2, 96, 8, 9, 10, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM);
                                    radix order 8-9-10: every exchange access conflict-free in scripts/smem_sim.py (8-10-9: 1.17x / 1.11x) */ \
