@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
 }
 
 // latspec [mmax][2][R][kp] -> y [R][nlat][nlon]   (persistent, with register prefetch of the next tile's spectrum)
-template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB>
+// TRUNC: 2 * mmax <= H, i.e. the partner X[H-q] of every retained order is beyond the truncation (zero): it is neither loaded nor multiplied.
+template <typename T, int ROWS, int GROUPS, int TPG, int R0, int R1, int R2, int MINB, bool TRUNC>
 __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(const float* __restrict__ Zs, T* __restrict__ y, const FftParams prm) {
   typedef CtGeom<ROWS, R0, R1, R2> G;
   typedef typename G::BufS BufS;
@@ -453,14 +454,15 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(co
       const int qd = item_quad(e), q = item_q(e), q2 = H - q;
       const int k = k0 + qd * 4;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      pa_r[it] = z; pa_i[it] = z; pb_r[it] = z; pb_i[it] = z;
+      pa_r[it] = z; pa_i[it] = z;
+      if (!TRUNC) { pb_r[it] = z; pb_i[it] = z; }
       if (e < NITEMS && q <= H / 2 && k < prm.kp) {
         if (q < mmax) {
           const float* src = Zs + (((size_t)q * 2) * prm.R + r) * prm.kp + k;
           pa_r[it] = __ldg(reinterpret_cast<const float4*>(src));
           pa_i[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp));
         }
-        if (q2 < mmax) {
+        if (!TRUNC && q2 < mmax) {
           const float* src = Zs + (((size_t)q2 * 2) * prm.R + r) * prm.kp + k;
           pb_r[it] = __ldg(reinterpret_cast<const float4*>(src));
           pb_i[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)prm.R * prm.kp));
@@ -504,6 +506,20 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(co
       const float hb = (prm.scale_mode == 1 && !b_self) ? 0.5f : 1.f;
       const float2 wq = twm[q];                                 // W_N^q
       const float ar[4] = {pa_r[it].x, pa_r[it].y, pa_r[it].z, pa_r[it].w}, ai[4] = {pa_i[it].x, pa_i[it].y, pa_i[it].z, pa_i[it].w};
+      if (TRUNC) {
+        // B = 0:  Z'[q] = A + i A conj(w),  Z'[H-q] = conj(A) + i conj(A) w, stored (im, re):
+        //   Z'[q]   = (Ai (1 + wy) + Ar wx,  Ar (1 + wy) - Ai wx)      Z'[H-q] = (Ar wx - Ai (1 - wy),  Ar (1 - wy) + Ai wx)
+        const float wp = 1.f + wq.y, wn = 1.f - wq.y;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          pr Ar = make_pr(ar[2 * i], ar[2 * i + 1]), Ai = a_self ? make_pr(0.f, 0.f) : make_pr(ai[2 * i], ai[2 * i + 1]);
+          if (prm.scale_mode == 1) { Ar = rmul(Ar, ha); Ai = rmul(Ai, ha); }
+          const BufB rowp = bB + (qd * 2 + i) * G::BSB;
+          rowp.st(s1, mk<cpair>(rfma(Ai, wp, rmul(Ar, wq.x)), rfma(Ai, -wq.x, rmul(Ar, wp))));
+          if (q != 0 && q2 != q) rowp.st(s2, mk<cpair>(rfma(Ai, -wn, rmul(Ar, wq.x)), rfma(Ai, wq.x, rmul(Ar, wn))));
+        }
+        continue;
+      }
       const float br[4] = {pb_r[it].x, pb_r[it].y, pb_r[it].z, pb_r[it].w}, bi[4] = {pb_i[it].x, pb_i[it].y, pb_i[it].z, pb_i[it].w};
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -741,7 +757,8 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
     B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, GROUPS * TPG, smem, st>>>(static_cast<const T*>(in), static_cast<float*>(out), prm);
   } else {
-    auto k = fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>;
+    auto k = (2 * pl->mmax <= G::H) ? fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB, true>
+                                    : fft_synthesis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB, false>;
     B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, GROUPS * TPG, smem, st>>>(static_cast<const float*>(in), static_cast<T*>(out), prm);
   }
