@@ -266,6 +266,17 @@ template <> struct RawPair<__nv_bfloat16> {
   __device__ __forceinline__ float2 get() const { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 };
 
+// barrier among the TPG threads of one row group (the stages between two block-wide passes touch only the group's own rows)
+// (immediate barrier ids: with a register id ptxas reserves all 16 named barriers of the CTA, which caps the CTAs per SM)
+template <int TPG, int GROUPS>
+__device__ __forceinline__ void group_sync(int grp) {
+  static_assert(GROUPS <= 4, "one named barrier per group");
+  if (GROUPS == 1 || grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(TPG) : "memory");
+  else if (grp == 1) asm volatile("bar.sync 2, %0;" ::"n"(TPG) : "memory");
+  else if (grp == 2) asm volatile("bar.sync 3, %0;" ::"n"(TPG) : "memory");
+  else asm volatile("bar.sync 4, %0;" ::"n"(TPG) : "memory");
+}
+
 __device__ __forceinline__ cpair pack_rows(float2 a, float2 b) { return mk<cpair>(make_pr(a.x, b.x), make_pr(a.y, b.y)); }
 
 // walk of the persistent CTA over the tiles (k tile, image r) without a division per tile
@@ -358,13 +369,13 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_analysis_ct_kernel(con
     }
     tw.next();
     if (tw.r < prm.R) load_tile(tw.kt, tw.r);   // in flight until the next iteration
-    __syncthreads();
+    group_sync<TPG, GROUPS>(grp);
     ct_stage<BufS, BufB, H, R1, R0, TPG, PPT>(bS, bB, tw1, G::BSS, G::BSB, t, prow0);
-    __syncthreads();
     if (R2 > 1) {
+      group_sync<TPG, GROUPS>(grp);
       ct_stage<BufB, typename G::BufI, H, (R2 > 1 ? R2 : 2), R0 * R1, TPG, PPT>(bB, typename G::BufI{bS.p}, tw2, G::BSB, G::BSS, t, prow0);
-      __syncthreads();
     }
+    __syncthreads();   // the split pass reads the rows of every group
     // ---- split + truncate + scale + store: X[m] = (Z[m] + conj Z[H-m]) / 2 + W_N^m (Z[m] - conj Z[H-m]) / (2i), two 16-byte stores
     auto split = [&](auto res, int stride) {
       typedef typename decltype(res)::layout L;
@@ -540,12 +551,12 @@ __global__ void __launch_bounds__(GROUPS * TPG, MINB) fft_synthesis_ct_kernel(co
     }
     tw.next();
     if (tw.r < prm.R) load_tile(tw.kt, tw.r);   // in flight until the next iteration
-    __syncthreads();
+    __syncthreads();   // the spectrum build wrote the rows of every group
     ct_stage<BufB, BufS, H, R0, 1, TPG, PPT>(bB, bS, nullptr, G::BSB, G::BSS, t, prow0);
-    __syncthreads();
+    group_sync<TPG, GROUPS>(grp);
     if (R2 > 1) {
       ct_stage<BufS, BufB, H, R1, R0, TPG, PPT>(bS, bB, tw1, G::BSS, G::BSB, t, prow0);
-      __syncthreads();
+      group_sync<TPG, GROUPS>(grp);
     }
     // ---- last stage fused with the store: butterfly j yields z[e], e = j + rr * NsL, (x[2e], x[2e+1]) = (Im, Re) of the swapped result
     auto last = [&](auto src, int stride) {
