@@ -492,13 +492,13 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": "tcgen05 kind::tf32, fp32 accumulate" if precision == "tf32" else "fp32 FMA (CUDA cores)",
                    "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "operator": "dhconv", "lmax": L, "mmax": M,
-                   "l2": "256 MiB buffer written between timed iterations (L2 flush); inputs 151 MB > 126 MB L2",
+                   "l2": f"256 MiB buffer written between timed iterations (L2 flush); input {x_host.numel() * x_host.element_size() / 1e6:.0f} MB",
                    "weight_relayout_in_step": True, "flops_fwd_bwd_nnz": flops_fwd_bwd(wl)},
         "clocks": clocks,
         "e2e": {"value": world * 1e3 / ms_e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": gw_host.numel() * 8,
-                "how": "makani_b200.HostFeed: every step copies its 151 MB input from pinned host memory and reads its weight gradient back; the copy of "
-                       "step i+1 (side stream, second device buffer) and the read-back of step i-1 overlap the kernels of step i; K steps timed from the "
-                       "first copy to the last read-back; inputs span 2 x 151 MB > L2",
+                "how": f"makani_b200.HostFeed: every step copies its {x_bytes / 1e6:.0f} MB input from pinned host memory and reads its weight gradient back; the "
+                       "copy of step i+1 (side stream, second device buffer) and the read-back of step i-1 overlap the kernels of step i; K steps timed "
+                       "from the first copy to the last read-back; two input buffers + gradients exceed the 126 MB L2",
                 "serial_value": world * 1e3 / ms_e2e_serial, "serial_ms_per_step": ms_e2e_serial,
                 "serial_how": "copy -> fwd+bwd -> read-back in one stream, L2 flushed between steps"},
         "gpu_launches": launches_per_step,

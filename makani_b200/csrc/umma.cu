@@ -780,15 +780,23 @@ static int fill_mix(const Plan* pl, int op, int B, int G, int Ci, int Co, MixPar
   return 0;
 }
 
+// Column tiling of a mix GEMM: one tile of up to 256 columns when that covers everything; otherwise equal tiles of at most 128
+// columns (no half-empty last tile -- at C = 384 a 256 + 128 split wasted a quarter of the MMAs -- and 2 N <= 256 TMEM columns per
+// complex accumulator leaves room for two accumulator sets, so the epilogue overlaps the next tile).
+static void split_cols(int cols, int gran, int* N, int* n_nt) {
+  if (cols <= 256) { *n_nt = 1; *N = round_up(cols, gran); return; }
+  *n_nt = ceil_div(cols, 128);
+  *N = round_up(ceil_div(cols, *n_nt), 32);   // the epilogues drain 32 columns at a time: a tile must not end inside a chunk
+}
+
 int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st) {
   MixParams p;
   int rc = fill_mix(pl, op, B, G, Ci, Co, &p);
   if (rc) return rc;
   p.out = y; p.cbias = static_cast<const float2*>(cbias);
   const int cols = p.Cog + ((p.cpo - Co) > 0 ? (p.cpo - Co) : 0);   // last group's tile also writes the zero padding
-  p.nblk = ceil_div(cols, 32) < 8 ? ceil_div(cols, 32) : 8;
-  p.N = 32 * p.nblk;
-  p.n_nt = ceil_div(cols, p.N);
+  split_cols(cols, 32, &p.N, &p.n_nt);
+  p.nblk = p.N / 32;
   p.idesc = make_idesc(p.N, 0, 1, 0);
   p.idesc_neg = make_idesc(p.N, 0, 1, 1);
   p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;
@@ -811,8 +819,7 @@ int mix_dgrad_umma(const Plan* pl, int op, const void* w, const float* gy, float
   if (rc) return rc;
   p.out = gx;
   const int cols = p.Cig + ((p.cpi - Ci) > 0 ? (p.cpi - Ci) : 0);
-  p.N = round_up(cols, 16) < 256 ? round_up(cols, 16) : 256;
-  p.n_nt = ceil_div(cols, p.N);
+  split_cols(cols, 16, &p.N, &p.n_nt);
   p.idesc = make_idesc(p.N, 0, 0, 0);
   p.idesc_neg = make_idesc(p.N, 0, 0, 1);
   const uint32_t bb = (uint32_t)round_up(p.N * 128, 1024);
@@ -832,9 +839,8 @@ int mix_wgrad_umma(const Plan* pl, int op, const float* x, const float* gy, floa
   int rc = fill_mix(pl, op, B, G, Ci, Co, &p);
   if (rc) return rc;
   p.out = gw;
-  p.nblk = ceil_div(p.cop, 32) < 8 ? ceil_div(p.cop, 32) : 8;
-  p.N = 32 * p.nblk;
-  p.n_nt = ceil_div(p.cop, p.N);
+  split_cols(p.cop, 32, &p.N, &p.n_nt);
+  p.nblk = p.N / 32;
   p.idesc = make_idesc(p.N, 1, 1, 0);
   p.idesc_neg = make_idesc(p.N, 1, 1, 1);
   p.offA_i = 16384; p.offB_r = 32768; p.offB_i = 32768 + 4096 * p.nblk;

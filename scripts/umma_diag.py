@@ -22,6 +22,7 @@ CASES = {
     "cfg2c": (721, 1440, 240, 241, "equiangular", 1, 73, 73, 1),
     "wide": (64, 128, 64, 65, "legendre-gauss", 1, 200, 136, 1),
     "cfg2a": (240, 480, 240, 241, "legendre-gauss", 1, 384, 384, 1),
+    "wide3": (64, 128, 64, 65, "legendre-gauss", 1, 300, 330, 1),     # three ragged column tiles
 }
 KERNELS = ["analysis", "synthesis", "mix_fwd", "mix_dgrad", "mix_wgrad"]
 
