@@ -1,7 +1,6 @@
 #!/bin/bash
 # Short GPU round trip: parity tests + headline bench (A/B of an FFT variant through B200SHT_FFT_VARIANT).
 mkdir -p gpurun_out
-timeout 600 python scripts/umma_diag.py all wide wide3 cfg2a tiles > gpurun_out/quick_diag.log 2>&1; grep -E "failures|FAIL|rc=1" gpurun_out/quick_diag.log | cut -c1-200 | tail -8
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_umma.py -m gpu -q -x --timeout=600 -k "not kernels_agree" 2>&1 | tail -15 > gpurun_out/quick_pytest.log
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err
 B200SHT_FFT_VARIANT=1 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu > gpurun_out/quick_bench_v1.json 2>> gpurun_out/quick_bench.err

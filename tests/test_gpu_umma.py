@@ -45,5 +45,13 @@ def test_spectral_conv_fwd_bwd_tf32(case):
     _run_conv_case(case, "tf32", 1e-3)
 
 
+# more than 256 channels: the mix GEMMs split their columns into several equal tiles (ragged last tile, 300 != 330)
+WIDE_CASE = (24, 48, "legendre-gauss", 24, 48, "legendre-gauss", 16, 17, 1, 300, 330, 1, "dhconv", False, True)
+
+
+def test_spectral_conv_many_channels_tf32():
+    _run_conv_case(WIDE_CASE, "tf32", 1e-3)
+
+
 def test_spectral_conv_bf16_tf32():
     _run_conv_case(CONV_CASES[1], "tf32", 1e-3, act_dtype=torch.bfloat16)
