@@ -780,7 +780,8 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
 // lengths with a compile-time plan: (ROWS, GROUPS, TPG, R0, R1, R2, CTAs/SM) for H = nlon / 2 = R0*R1*R2.  R0 is a power of two <= 16
 // (LaySkew); TPG >= H/R0, ~ max_s H/R_s.  Other lengths (odd, or not listed) run the runtime-plan kernels.
 #define CT_PLANS(X)             \
-  X(4, 2, 96, 8, 9, 10, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis -10% vs 8-row tiles at 2 CTAs/SM);
+  X(4, 2, 96, 8, 9, 10, 3)      /* nlon 1440: 4-row tiles, 2 groups x one row pair per thread, 3 CTAs/SM (measured: synthesis 149 us; 8-row tiles at 2 CTAs/SM 175 us,
+                                   4 CTAs/SM at <= 80 registers 186 us);
                                    radix order 8-9-10: every exchange access conflict-free in scripts/smem_sim.py (8-10-9: 1.17x / 1.11x) */ \
   X(8, 4, 96, 8, 9, 5, 2)       /* nlon  720 */ \
   X(8, 4, 64, 8, 5, 6, 2)       /* nlon  480 */ \
