@@ -33,6 +33,9 @@ What is restated here (pure PyTorch on CPU, fp32 or fp64 selectable):
 PARITY PINNING STATUS
   * contractions + ComplexReLU: pinned element-wise against the reference's own files, imported in the build
     container by tests/golden/make_golden.py  ->  tests/golden/contractions_golden.npz.
+  * spectral_conv_forward: pinned element-wise (output, resampled residual, every gradient) against the reference's own
+    SpectralConv class, imported by path with its package imports stubbed and run on this file's transforms
+    (tests/golden/make_golden.py  ->  tests/golden/spectral_conv_golden.npz; tests/test_oracle.py).
   * RealSHT / InverseRealSHT: "PARITY UNPINNED" element-wise against torch-harmonics (package absent, no
     network).  Pinned instead by (a) every invariant the reference's tests encode (Parseval, H1 = l(l+1) L2,
     constant field -> only l=0, quadrature sums, GRF variance), (b) an independent implementation of Y_l^m

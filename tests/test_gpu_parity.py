@@ -6,6 +6,7 @@ so a purely relative element-wise bound is not meaningful; the reference's own c
 """
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -266,6 +267,40 @@ def test_contractions_match_reference_golden():
         y = _mix_via_kernels(xa, torch.from_numpy(g[f"w_{name}"]), op, cbias=cb)
         ref = (torch.einsum("bixy,io->boxy" if name == "shared" else "bixy,xio->boxy", xa, torch.from_numpy(g[f"w_{name}"])) + cb) * tri
         assert torch.allclose(y, ref, atol=1e-5, rtol=1e-4), name + "+bias"
+
+
+CONV_GOLD = os.path.join(os.path.dirname(__file__), "golden", "spectral_conv_golden.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import CONV_GOLDEN_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CONV_GOLDEN_CASES))
+def test_spectral_conv_matches_reference_class_golden(name):
+    """The CUDA SpectralConv against the output / gradients of the REFERENCE's SpectralConv class (tests/golden/make_golden.py runs
+    /root/reference/makani/models/common/spectral_convolution.py on the oracle transforms): fp32 path, rtol 1e-5."""
+    g = np.load(CONV_GOLD)
+    nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, lmax, mmax, B, Cin, Cout, G, op, sep, bias = CONV_GOLDEN_CASES[name]
+    f = mb.RealSHT(nlat_i, nlon_i, lmax, mmax, grid_i, precision="fp32")
+    i = mb.InverseRealSHT(nlat_o, nlon_o, lmax, mmax, grid_o, precision="fp32")
+    conv = mb.SpectralConv(f, i, Cin, Cout, num_groups=G, operator_type=op, separable=sep, bias=bias, precision="fp32").to(DEV)
+    assert list(conv.weight.shape) == list(g[f"{name}/weight_shape"])
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(g[f"{name}/weight"]))
+        if bias:
+            conv.bias.copy_(torch.from_numpy(g[f"{name}/bias"]))
+    x = torch.from_numpy(g[f"{name}/x"]).to(DEV).requires_grad_(True)
+    y, res = conv(x)
+    rt = 2e-5
+    close(y, torch.from_numpy(g[f"{name}/y"]), rt, f"golden {name} y")
+    loss = (y * torch.from_numpy(g[f"{name}/gy"]).to(DEV)).sum()
+    if f"{name}/residual" in g:
+        close(res, torch.from_numpy(g[f"{name}/residual"]), rt, f"golden {name} residual")
+        loss = loss + (res * torch.from_numpy(g[f"{name}/gres"]).to(DEV)).sum()
+    loss.backward()
+    close(x.grad, torch.from_numpy(g[f"{name}/dx"]), rt, f"golden {name} dx")
+    close(conv.weight.grad, torch.from_numpy(g[f"{name}/dweight"]), rt, f"golden {name} dweight")
+    if bias:
+        close(conv.bias.grad, torch.from_numpy(g[f"{name}/dbias"]), 1e-4, f"golden {name} dbias")
 
 
 def test_complex_relu_matches_reference_golden():

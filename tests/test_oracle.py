@@ -2,6 +2,7 @@
 Y_l^m implementation (scipy), analytic harmonics, and the golden vectors generated from the reference's files."""
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -162,6 +163,39 @@ def test_complex_relu_against_reference_golden():
         bias = torch.from_numpy(g[f"relu_bias_{mode}"]) if f"relu_bias_{mode}" in g else 0.0
         y = O.complex_relu(z, mode=mode, bias=bias, negative_slope=0.1)
         assert torch.allclose(y, torch.from_numpy(g[f"relu_{mode}"]), atol=1e-6, rtol=1e-5), mode
+
+
+CONV_GOLD = os.path.join(os.path.dirname(__file__), "golden", "spectral_conv_golden.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden import CONV_GOLDEN_CASES  # noqa: E402  (case table only; the generator itself needs /root/reference)
+
+
+@pytest.mark.parametrize("name", sorted(CONV_GOLDEN_CASES))
+def test_spectral_conv_against_reference_class_golden(name):
+    """oracle.spectral_conv_forward == the REFERENCE's SpectralConv class (spectral_convolution.py:116-264, run by
+    tests/golden/make_golden.py on the oracle transforms): output, resampled residual and all gradients."""
+    g = np.load(CONV_GOLD)
+    nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, lmax, mmax, B, Cin, Cout, G, op, sep, bias = CONV_GOLDEN_CASES[name]
+    sht = O.RealSHT(nlat_i, nlon_i, lmax, mmax, grid_i)
+    isht = O.InverseRealSHT(nlat_o, nlon_o, lmax, mmax, grid_o)
+    x = torch.from_numpy(g[f"{name}/x"]).requires_grad_(True)
+    w = torch.from_numpy(g[f"{name}/weight"]).requires_grad_(True)
+    assert list(w.shape) == list(g[f"{name}/weight_shape"])
+    b = torch.from_numpy(g[f"{name}/bias"]).requires_grad_(True) if bias else None
+    y, res = O.spectral_conv_forward(x, w, sht, isht, num_groups=G, operator_type=op, separable=sep, bias=b)
+    tol = dict(atol=2e-5, rtol=1e-4)
+    assert torch.allclose(y, torch.from_numpy(g[f"{name}/y"]), **tol)
+    loss = (y * torch.from_numpy(g[f"{name}/gy"])).sum()
+    if f"{name}/residual" in g:
+        assert torch.allclose(res, torch.from_numpy(g[f"{name}/residual"]), **tol)
+        loss = loss + (res * torch.from_numpy(g[f"{name}/gres"])).sum()
+    else:
+        assert res is x
+    loss.backward()
+    assert torch.allclose(x.grad, torch.from_numpy(g[f"{name}/dx"]), **tol)
+    assert torch.allclose(w.grad, torch.from_numpy(g[f"{name}/dweight"]), atol=1e-4, rtol=1e-4)
+    if bias:
+        assert torch.allclose(b.grad, torch.from_numpy(g[f"{name}/dbias"]), atol=1e-3, rtol=1e-4)
 
 
 def test_spectral_conv_oracle_shapes_and_residual():
