@@ -159,6 +159,26 @@ def conv_golden():
     print("wrote", path, len(out), "arrays", os.path.getsize(path), "bytes")
 
 
+def check_attention_raises():
+    """the reference's SpectralAttention.forward cannot run (its einsums get 5-D operands); recorded here so that the
+    "intended semantics, parity unpinned" status of makani_b200.SpectralAttention stays checkable."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import makani_oracle as O
+
+    ref = _load_reference_spectral_conv()
+    sht, isht = O.RealSHT(12, 24, 8, 8, "legendre-gauss"), O.InverseRealSHT(12, 24, 8, 8, "legendre-gauss")
+    for op in ("diagonal", "l-dependant"):
+        try:
+            att = ref.SpectralAttention(sht, isht, 4, 4, operator_type=op, hidden_size_factor=2, complex_activation="real", spectral_layers=1)
+            att(torch.randn(2, 4, 12, 24))
+            print(f"reference SpectralAttention({op}) RUNS now: generate golden vectors for it")
+        except Exception as e:  # noqa: BLE001
+            print(f"reference SpectralAttention({op}) raises {type(e).__name__}: {str(e)[:120]}")
+
+
 if __name__ == "__main__":
     main()
     conv_golden()
+    check_attention_raises()
