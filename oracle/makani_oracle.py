@@ -36,6 +36,9 @@ PARITY PINNING STATUS
   * spectral_conv_forward: pinned element-wise (output, resampled residual, every gradient) against the reference's own
     SpectralConv class, imported by path with its package imports stubbed and run on this file's transforms
     (tests/golden/make_golden.py  ->  tests/golden/spectral_conv_golden.npz; tests/test_oracle.py).
+  * the reference's own test classes that go through torch_harmonics (tests/test_losses.py spectral losses, test_grids.py,
+    test_noise.py: 193 tests) run unmodified against this file posed as `torch_harmonics` and pass
+    (tests/reference_suites/run_reference_tests.py, report.txt).
   * RealSHT / InverseRealSHT: "PARITY UNPINNED" element-wise against torch-harmonics (package absent, no
     network).  Pinned instead by (a) every invariant the reference's tests encode (Parseval, H1 = l(l+1) L2,
     constant field -> only l=0, quadrature sums, GRF variance), (b) an independent implementation of Y_l^m
