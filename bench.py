@@ -469,7 +469,7 @@ def run_gpu_arm(args):
 
     # CPU baseline beside it (bounded sample: 1 warm-up + 2 timed steps of the same workload)
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # reported at N = 1 only (the other ranks have left; the scaling runs need not wait for it)
         cores, avail = pick_cpu_threads()
         t = cpu_reference_steps(wl, 1, 1, act_dtype)
         cpu = {"value": 1.0 / t, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -479,7 +479,7 @@ def run_gpu_arm(args):
     # The library path the reference runs on a GPU (cuFFT + cuBLAS einsum, allow_tf32=True as makani/train.py:87), timed on this
     # B200 with the same restated modules (the real torch-harmonics is not installable): informational, never the product path.
     lib = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         try:
             lib = gpu_library_baseline(wl, act_dtype, dev, flush)
         except Exception as e:  # pragma: no cover
