@@ -366,7 +366,6 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev = None
     try:
-        import makani_b200.sht as _s, makani_b200.spectral_convolution as _c
         dp_step()  # first call builds plans / tables
         torch.cuda.synchronize()
         _lib.call = counting_call

@@ -12,7 +12,6 @@ choreography is unit-tested on CPU with gloo against the serial oracle.
 """
 import ctypes
 
-import numpy as np
 import torch
 import torch.distributed as dist
 import torch.nn as nn
