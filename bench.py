@@ -58,6 +58,25 @@ def stage_bytes(wl, act_bytes):
     }
 
 
+def stage_flops(wl):
+    """Algorithmic flops per launch of the contraction stages (structurally non-zero l >= m pairs only), B = 1."""
+    nlat_i, _, _, nlat_o, _, _, L, M, C = WORKLOADS[wl]
+    nnz = nnz_modes(L, M)
+    mix = 8 * C * C * nnz
+    return {"legendre_analysis_in": 4 * C * nlat_i * nnz, "legendre_synthesis_out": 4 * C * nlat_o * nnz, "legendre_analysis_out": 4 * C * nlat_o * nnz,
+            "legendre_synthesis_in": 4 * C * nlat_i * nnz, "mix_forward": mix, "mix_backward": 2 * mix}
+
+
+def add_stage_tflops(stages, wl):
+    """annotate the per-stage records of the contraction kernels with their algorithmic TFLOP/s (metric (ii) of SURVEY section 8d)"""
+    fl = stage_flops(wl)
+    for name, rec in stages.items():
+        if name in fl and rec.get("ms"):
+            rec["alg_GFLOP"] = round(fl[name] / 1e9, 3)
+            rec["TFLOPs"] = round(fl[name] / (rec["ms"] * 1e-3) / 1e12, 2)
+    return stages
+
+
 def flops_fwd_bwd(wl):
     nlat_i, _, _, nlat_o, _, _, L, M, C = WORKLOADS[wl]
     nnz = nnz_modes(L, M)
@@ -445,6 +464,10 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
+    try:
+        add_stage_tflops(stages, wl)
+    except Exception:  # never lose the line over an annotation
+        pass
     peak, peak_src = measured_peaks()
     roof = None
     if stages:
