@@ -339,6 +339,35 @@ def run_gpu_arm(args):
             ms = tt.item()
         return ms
 
+    graph_info = None
+
+    def try_cuda_graph():
+        """Capture one fwd+bwd step (weight re-layout included) into a CUDA graph and time its replay.  Returns a dict for the JSON
+        line; any failure is reported there and never affects the eager numbers."""
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step(x_dev)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            step(x_dev)
+            ref_gw = conv.weight.grad.detach().clone()
+            conv.weight.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_gx = step(x_dev)
+            g.replay()
+            torch.cuda.synchronize()
+            same = torch.allclose(torch.view_as_real(conv.weight.grad), torch.view_as_real(ref_gw), rtol=1e-5, atol=1e-6) and bool(torch.isfinite(static_gx.float()).all())
+            if not same:
+                return {"ok": False, "why": "replay does not reproduce the eager weight gradient"}
+            ms = timed(g.replay, args.steps, args.warmup)
+            return {"ok": True, "ms_per_step": ms, "value": 1e3 / ms}
+        except Exception as e:  # noqa: BLE001
+            return {"ok": False, "why": str(e)[:300]}
+
     def timed(fn, steps, warmup, use_flush=True):
         for _ in range(warmup):
             fn()
@@ -401,6 +430,9 @@ def run_gpu_arm(args):
                 step(x_dev)  # local load only: no collective here, the other ranks are waiting at the next barrier
                 torch.cuda.synchronize()
         ms_dev = timed(dp_step, args.steps, args.warmup)
+        # opt-in (round-2 experiment, not part of the default line): the same step replayed from a CUDA graph, reported separately
+        if args.graph and world == 1:
+            graph_info = try_cuda_graph()
         if sampler:
             n_before = len(sampler.lines)
             t_wait = time.perf_counter()
@@ -530,6 +562,8 @@ def run_gpu_arm(args):
         "gpu_library_baseline": lib,
         "tflops_nnz": flops_fwd_bwd(wl) / (ms_dev * 1e-3) / 1e12,
     }
+    if graph_info is not None:
+        line["cuda_graph_replay"] = graph_info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -546,6 +580,7 @@ def main():
     ap.add_argument("--act", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stages", action="store_true", help="skip per-stage kernel timing")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph (opt-in experiment, N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
