@@ -121,6 +121,7 @@ def install_environment():
                 for i, c in enumerate(cases):
                     args = tuple(c) if isinstance(c, (list, tuple)) else (c,)
                     loc[f"{f.__name__}_{i}"] = (lambda a: (lambda self: f(self, *a)))(args)
+                loc[f"_orig_{f.__name__}"] = f      # the undecorated method, for debugging a single case by hand
                 return None
             return deco
 

@@ -49,3 +49,19 @@ def test_reference_sfno_network_builds_unchanged_on_makani_b200():
         assert a["params"][name] == b["params"][name], (name, a["params"][name], b["params"][name])
     assert all(c.startswith("makani_b200.") for c in b["spectral_classes"]), b["spectral_classes"]
     assert any(c.endswith("SpectralConv") for c in b["spectral_classes"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests/distributed"), reason="reference tree not mounted")
+def test_reference_distributed_spectral_conv_case_on_gloo():
+    """One (odd-size, uneven 46/45 + 91/90 split) case of the reference's own distributed SpectralConv test, unmodified, on 2 gloo ranks
+    against makani_b200.distributed.  All six cases on 2x1, 1x2 and 2x2: tests/reference_suites/report_distributed.txt
+    (RUN_REFERENCE_DISTRIBUTED=1 runs the six cases on 2x1 here, ~3 min)."""
+    import subprocess
+
+    script = os.path.join(HERE, "reference_suites", "run_reference_distributed.py")
+    env = dict(os.environ)
+    if not os.environ.get("RUN_REFERENCE_DISTRIBUTED"):
+        env["REFDIST_DEBUG_CASE"] = "91,180,91,180,1,4,1e-4"
+    r = subprocess.run([sys.executable, script, "2", "1"], capture_output=True, text=True, timeout=1500, env=env)
+    tail = "\n".join((r.stdout + r.stderr).strip().splitlines()[-12:])
+    assert r.returncode == 0 and "TOTAL grid 2x1: OK" in r.stdout, tail
