@@ -174,9 +174,17 @@ def worker(rank, world, port, h, w, q):
 
         torch.manual_seed, torch.randn, torch.randn_like = manual_seed, randn, randn_like
         loader = unittest.defaultTestLoader
-        names = [n for n in loader.getTestCaseNames(M.TestDistributedLayers) if n.startswith("test_distributed_spectral_conv")]
-        suite = unittest.TestSuite(M.TestDistributedLayers(n) for n in names)
-        M.TestDistributedLayers.setUpClass()
+        if os.environ.get("REFDIST_SUITE") == "losses":
+            # second pin at the SHT boundary: the spectral losses through thd.DistributedRealSHT == through the local transform
+            ML = importlib.import_module("tests.distributed.tests_distributed_losses")
+            Case = ML.TestDistributedLoss
+            keys = ("spectral", "sobolev", "coherence", "quadrature")
+            names = [n for n in loader.getTestCaseNames(Case) if any(k in n for k in keys)]
+        else:
+            Case = M.TestDistributedLayers
+            names = [n for n in loader.getTestCaseNames(Case) if n.startswith("test_distributed_spectral_conv")]
+        suite = unittest.TestSuite(Case(n) for n in names)
+        Case.setUpClass()
         if os.environ.get("REFDIST_DEBUG_CASE"):
             a = [float(v) if "e" in v or "." in v else int(v) for v in os.environ["REFDIST_DEBUG_CASE"].split(",")]
             inst = M.TestDistributedLayers("test_distributed_spectral_conv_0")
