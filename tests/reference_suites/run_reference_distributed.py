@@ -180,6 +180,12 @@ def worker(rank, world, port, h, w, q):
             Case = ML.TestDistributedLoss
             keys = ("spectral", "sobolev", "coherence", "quadrature")
             names = [n for n in loader.getTestCaseNames(Case) if any(k in n for k in keys)]
+        elif os.environ.get("REFDIST_SUITE") == "fft":
+            # the reference's own DistributedRealFFT1/2/3 (makani/mpu/fft.py) call torch_harmonics.distributed's transposes as plain
+            # functions (mpu/fft.py:59,169): here those are makani_b200.distributed's
+            MF = importlib.import_module("tests.distributed.tests_distributed_fft")
+            Case = MF.TestDistributedRealFFT
+            names = list(loader.getTestCaseNames(Case))
         else:
             Case = M.TestDistributedLayers
             names = [n for n in loader.getTestCaseNames(Case) if n.startswith("test_distributed_spectral_conv")]
