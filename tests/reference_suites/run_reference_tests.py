@@ -2,8 +2,9 @@
 """Run the REFERENCE's own test classes that exercise torch-harmonics' RealSHT / InverseRealSHT / quadrature against the oracle.
 
 torch-harmonics is not installable in this environment, and `import makani` needs physicsnemo / h5py / zarr / ruamel.  This script
-poses `oracle/makani_oracle.py` as the `torch_harmonics` package (RealSHT, InverseRealSHT, quadrature), `makani_b200.distributed`
-as `torch_harmonics.distributed` (primitives, split helpers), stubs the packages the reference imports but these tests never call
+poses `oracle/makani_oracle.py` as the `torch_harmonics` package (RealSHT, InverseRealSHT), the product module `makani_b200.quadrature`
+as `torch_harmonics.quadrature` (REFTESTS_ORACLE_QUADRATURE=1: the oracle's), `makani_b200.distributed` as `torch_harmonics.distributed`
+(primitives, split helpers), stubs the packages the reference imports but these tests never call
 (h5py, zarr, properscoring, parameterized, makani.utils.comm / YParams, the heavy `makani/__init__` files) and then imports the test
 modules from /root/reference/tests unmodified and runs the listed unittest classes.  Nothing is copied: the reference's loss / grid /
 noise code and its test expectations (Parseval, H1 = l(l+1) L2, quadrature sums to 4 pi, GRF variance, spectral CRPS identities ...)
@@ -56,7 +57,13 @@ def install_environment():
     quad.legendre_gauss_weights = as_torch(O.legendre_gauss_weights)
     quad.clenshaw_curtiss_weights = as_torch(O.clenshaw_curtiss_weights)
     quad.precompute_latitudes = as_torch(O.precompute_latitudes)
-    th.quadrature, th.distributed = quad, thd
+    if os.environ.get("REFTESTS_ORACLE_QUADRATURE"):
+        th.quadrature = quad                      # the oracle's quadrature functions
+    else:
+        import makani_b200.quadrature as mbq      # PRODUCT code (pure torch / numpy, runs without a GPU): what the shim installs
+
+        th.quadrature = quad = mbq
+    th.distributed = thd
     sys.modules.update({"torch_harmonics": th, "torch_harmonics.quadrature": quad, "torch_harmonics.distributed": thd,
                         "torch_harmonics.distributed.primitives": thdp})
 
