@@ -186,6 +186,11 @@ def worker(rank, world, port, h, w, q):
             MF = importlib.import_module("tests.distributed.tests_distributed_fft")
             Case = MF.TestDistributedRealFFT
             names = list(loader.getTestCaseNames(Case))
+        elif os.environ.get("REFDIST_SUITE") == "layers_all":
+            # every test of the class: the non-spectral ones (distributed MLP, instance / layer norms) reach makani_b200 only through
+            # makani/mpu/mappings.py, which imports _gather / _split / _reduce / _transpose from torch_harmonics.distributed.primitives
+            Case = M.TestDistributedLayers
+            names = list(loader.getTestCaseNames(Case))
         else:
             Case = M.TestDistributedLayers
             names = [n for n in loader.getTestCaseNames(Case) if n.startswith("test_distributed_spectral_conv")]
