@@ -28,6 +28,10 @@ CFG = dict(inp_shape=(33, 64), out_shape=(33, 64), inp_chans=5, out_chans=3, emb
            model_grid_type="equiangular", sht_grid_type="legendre-gauss", bias=True)
 
 
+# the non-linear spectral filter (SpectralAttention): the reference constructs it (only its forward raises)
+CFG_NONLINEAR = dict(CFG, filter_type="non-linear", operator_type="diagonal", num_layers=2)
+
+
 def stub_physicsnemo():
     pn = types.ModuleType("physicsnemo")
 
@@ -74,11 +78,12 @@ def main():
     torch.manual_seed(333)
     from makani.models.networks import sfnonet
 
-    net = sfnonet.SphericalFourierNeuralOperatorNet(**CFG)
+    cfg = CFG_NONLINEAR if (len(sys.argv) > 2 and sys.argv[2] == "nonlinear") else CFG
+    net = sfnonet.SphericalFourierNeuralOperatorNet(**cfg)
     info = describe(net)
     info["spectral_classes"] = sorted({type(m).__module__ + "." + type(m).__name__ for m in net.modules()
-                                       if type(m).__name__ in ("SpectralConv", "RealSHT", "InverseRealSHT")})
-    if which == "a":
+                                       if type(m).__name__ in ("SpectralConv", "SpectralAttention", "RealSHT", "InverseRealSHT")})
+    if which == "a" and cfg is CFG:
         y = net(torch.randn(1, CFG["inp_chans"], *CFG["inp_shape"]))
         info["forward_shape"] = list(y.shape)
     print(json.dumps(info))

@@ -28,7 +28,8 @@ def test_committed_report_is_green():
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/makani"), reason="reference tree not mounted")
-def test_reference_sfno_network_builds_unchanged_on_makani_b200():
+@pytest.mark.parametrize("variant", ["linear", "nonlinear"])
+def test_reference_sfno_network_builds_unchanged_on_makani_b200(variant):
     """the reference's SphericalFourierNeuralOperatorNet, unmodified, constructed on the makani_b200 shim exposes the
     same parameters (names, shapes, dtypes, model-parallel tags) and state-dict keys as on the reference semantics (oracle)."""
     import json
@@ -37,18 +38,19 @@ def test_reference_sfno_network_builds_unchanged_on_makani_b200():
     script = os.path.join(HERE, "reference_suites", "build_reference_sfno.py")
     infos = {}
     for which in ("a", "b"):
-        r = subprocess.run([sys.executable, script, which], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, script, which, variant], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
         infos[which] = json.loads(r.stdout.strip().splitlines()[-1])
     a, b = infos["a"], infos["b"]
-    assert a["forward_shape"] == [1, 3, 33, 64]
+    if variant == "linear":      # the reference's SpectralAttention.forward raises: construction only for "nonlinear"
+        assert a["forward_shape"] == [1, 3, 33, 64]
     assert a["state_dict_keys"] == b["state_dict_keys"]
     assert not any("weights" in k or "pct" in k for k in b["state_dict_keys"])      # SHT tables are not checkpointed
     assert a["params"].keys() == b["params"].keys()
     for name in a["params"]:
         assert a["params"][name] == b["params"][name], (name, a["params"][name], b["params"][name])
     assert all(c.startswith("makani_b200.") for c in b["spectral_classes"]), b["spectral_classes"]
-    assert any(c.endswith("SpectralConv") for c in b["spectral_classes"])
+    assert any(c.endswith("SpectralConv" if variant == "linear" else "SpectralAttention") for c in b["spectral_classes"])
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tests/distributed"), reason="reference tree not mounted")
