@@ -26,7 +26,7 @@
  *
  * Internal ("packed") tensor formats -- opaque to callers that only use the *_sht_* / spectral_conv entry points,
  * documented in DESIGN.md section 3:
- *   latspec  float [mmax][2][B*C][kp]           (after the longitude FFT;  kp = nlat rounded up to 8)
+ *   latspec  float [mmax8][2][B*C][kp]          (after the longitude FFT;  kp = nlat rounded up to 8, mmax8 = mmax rounded up to 8)
  *   spec     float [lmax][mmax][2][B][cp]       (spectral coefficients;    cp = C rounded up to 4)
  */
 #ifndef B200SHT_H
@@ -84,7 +84,8 @@ int b200sht_plan_create(b200sht_plan** plan, int nlat, int nlon, int lmax, int m
 int b200sht_plan_create_ex(b200sht_plan** plan, int nlat, int nlon, int lmax, int mmax, int m_offset, int flags,
                            const double* cost, const double* quad_w, int csphase, void* stream);
 int b200sht_plan_destroy(b200sht_plan* plan);
-/* what: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 path available (0/1), 7 m_offset */
+/* what: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 path available (0/1), 7 m_offset,
+ *       8 tensor-core longitude DFT available for this grid (0/1) */
 int64_t b200sht_plan_query(const b200sht_plan* plan, int what);
 /* device pointer to the fp32 table [mmax][lmax][kp] (for tests) */
 const float* b200sht_plan_table(const b200sht_plan* plan);
@@ -101,12 +102,17 @@ int64_t b200sht_spec_elems_lm(int L, int M, int B, int C);
  *   X[m][p][r][k] = row_scale[k] * mode_scale[m] * sum_j x[r][k][j] exp(-2 pi i m j / nlon)
  * scale_mode 0: SHT forward     (row_scale = quad_w[k] * 2 pi / nlon, mode_scale = 1)
  * scale_mode 1: adjoint of irfft (row_scale = 1, mode_scale = 1 for m = 0 and Nyquist, 2 otherwise)
- * scale_mode | 2: additionally round the output to the nearest TF32 value (it is the operand of a kind::tf32 GEMM) */
+ * scale_mode | 2: TF32 precision: the output is rounded to the nearest TF32 value (it is the operand of a kind::tf32 GEMM) and,
+ *                 for nlon = 8 * N2 <= 1520 and mmax <= 256, the transform itself runs on the tensor cores (radix-8 butterflies on
+ *                 the CUDA cores x a [mmax/8 x nlon/16] DFT matrix as a kind::tf32 GEMM, csrc/dft.cu) */
 int b200sht_fft_analysis(const b200sht_plan* plan, const void* x, int dtype, int B, int C,
                          float* latspec, int scale_mode, void* stream);
 /* Longitude synthesis: truncated half spectrum -> real rows (+ optional per-channel bias, cast to dtype).
  * scale_mode 0: irfft(norm="forward") semantics (imaginary part of m=0 / Nyquist ignored)
- * scale_mode 1: adjoint of the scale_mode-0 analysis (row_scale = quad_w[k] 2 pi/nlon, modes m>0 halved) */
+ * scale_mode 1: adjoint of the scale_mode-0 analysis (row_scale = quad_w[k] 2 pi/nlon, modes m>0 halved)
+ * scale_mode | 2: TF32 precision (tensor-core DFT where the grid allows, see above).  That path reads the orders in residue classes
+ *                 modulo 8, so `latspec` must have room for round_up(mmax, 8) orders (b200sht_latspec_elems does) and the call
+ *                 CLEARS the padding orders mmax .. round_up(mmax, 8) - 1 of `latspec` (the only write to an input buffer in the API). */
 int b200sht_fft_synthesis(const b200sht_plan* plan, const float* latspec, void* y, int dtype, int B, int C,
                           const float* bias, int scale_mode, void* stream);
 /* Legendre analysis  spec[l][m][..] = sum_k P[m][l][k] latspec[m][..][k]   (l >= 32*floor(m/32)) */
@@ -202,6 +208,10 @@ int b200sht_spectral_conv_forward_host(const b200sht_plan* fwd, const b200sht_pl
 /* direction 0: rows a, b (float[N]) -> half spectra Xa, Xb (float[2*mmax], interleaved), unscaled rfft.
  * direction 1: half spectra (float[2*mmax]) -> rows (float[N]), irfft(norm="forward") semantics. */
 int b200sht_debug_fft_host(int N, int mmax, int direction, const float* in_a, const float* in_b, float* out_a, float* out_b);
+/* the tensor-core DFT's factorisation (radix-8 stage, twiddles, index maps: the same __host__ __device__ code as the kernels) with the
+ * GEMM summed in double on the host.  direction 0: in float[N] -> out float[2*mmax] (interleaved); direction 1: the reverse.
+ * scale_mode / row_scale as for b200sht_fft_analysis / _synthesis (row_scale = the row's quadrature factor). */
+int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float row_scale, const float* in, float* out);
 /* radices chosen for length N; returns the number of stages or a negative status */
 int b200sht_debug_fft_plan(int N, int* radices, int max_radices);
 /* table [mmax][lmax][nlat] (fp32) from cos(colatitude) cost[nlat] */

@@ -39,6 +39,9 @@ int complex_relu_bwd(const Plan* pl, int mode, const float* x, const float* bias
 // tcgen05 path (umma.cu)
 int umma_plan_init(Plan* pl);
 void umma_plan_destroy(Plan* pl);
+int dft_plan_init(Plan* pl);
+void dft_plan_destroy(Plan* pl);
+int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out);
 int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
 int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st);
 int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
@@ -122,6 +125,7 @@ int b200sht_plan_create_ex(b200sht_plan** out, int nlat, int nlon, int lmax, int
     return rc ? rc : B200SHT_ERR_CUDA;
   }
   pl->umma_ok = (!pl->no_table && umma_plan_init(pl) == 0) ? 1 : 0;
+  dft_plan_init(pl);   // optional: leaves dft_state null when the grid is outside the tensor-core DFT's range
   *out = pl;
   return 0;
 }
@@ -129,6 +133,7 @@ int b200sht_plan_create_ex(b200sht_plan** out, int nlat, int nlon, int lmax, int
 int b200sht_plan_destroy(b200sht_plan* pl) {
   if (!pl) return 0;
   umma_plan_destroy(pl);
+  dft_plan_destroy(pl);
   cudaFree(pl->d_table);
   cudaFree(pl->d_rowscale);
   cudaFree(pl->d_twiddle);
@@ -147,6 +152,7 @@ int64_t b200sht_plan_query(const b200sht_plan* pl, int what) {
     case 5: return (int64_t)sizeof(float) * pl->mmax * pl->lmax * pl->kp;
     case 6: return pl->umma_ok;
     case 7: return pl->m0;
+    case 8: return pl->dft_state != nullptr;
     default: return -1;
   }
 }
@@ -158,7 +164,8 @@ int b200sht_plan_copy_table(const b200sht_plan* pl, float* dst, void* stream) {
   return 0;
 }
 
-int64_t b200sht_latspec_elems(const b200sht_plan* pl, int B, int C) { return (int64_t)pl->mmax * 2 * B * C * pl->kp; }
+// orders are padded to a multiple of 8: the tensor-core DFT reads the latspec planes in residue classes m = c + 8 * m2
+int64_t b200sht_latspec_elems(const b200sht_plan* pl, int B, int C) { return (int64_t)round_up(pl->mmax, 8) * 2 * B * C * pl->kp; }
 int64_t b200sht_spec_elems(const b200sht_plan* pl, int B, int C) { return (int64_t)pl->lmax * pl->mmax * 2 * B * cp_of(C); }
 int64_t b200sht_spec_elems_lm(int L, int M, int B, int C) { return (int64_t)L * M * 2 * B * cp_of(C); }
 
@@ -172,7 +179,7 @@ int b200sht_fft_analysis(const b200sht_plan* pl, const void* x, int dtype, int B
 int b200sht_fft_synthesis(const b200sht_plan* pl, const float* latspec, void* y, int dtype, int B, int C, const float* bias, int scale_mode,
                           void* stream) {
   B200_REQUIRE(pl && y && latspec, "fft_synthesis: null argument");
-  B200_REQUIRE(scale_mode == 0 || scale_mode == 1, "fft_synthesis: bad scale_mode %d", scale_mode);
+  B200_REQUIRE(scale_mode >= 0 && scale_mode <= 3, "fft_synthesis: bad scale_mode %d", scale_mode);
   return fft_synthesis(pl, latspec, y, dtype, B, C, bias, scale_mode, S(stream));
 }
 
@@ -270,7 +277,7 @@ int b200sht_sht_inverse(const b200sht_plan* pl, const void* coeffs, void* y, int
   split_ws(pl, B, C, ws, &Z, &sp);
   int rc = b200sht_spec_pack(pl->lmax, pl->mmax, coeffs, sp, B, C, stream);
   if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(pl, Z, y, dtype, B, C, nullptr, 0, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, Z, y, dtype, B, C, nullptr, 0 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   return rc;
 }
 
@@ -281,7 +288,7 @@ int b200sht_sht_forward_adjoint(const b200sht_plan* pl, const void* gcoeffs, voi
   split_ws(pl, B, C, ws, &Z, &sp);
   int rc = b200sht_spec_pack(pl->lmax, pl->mmax, gcoeffs, sp, B, C, stream);
   if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(pl, Z, gx, dtype, B, C, nullptr, 1, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, Z, gx, dtype, B, C, nullptr, 1 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   return rc;
 }
 
@@ -406,16 +413,17 @@ int b200sht_spectral_conv_forward(const b200sht_plan* f, const b200sht_plan* v, 
   if (rc) return rc;
   B200_REQUIRE(x && w && y && workspace, "spectral_conv_forward: null argument");
   ConvWs ws = conv_ws(f, v, d, workspace);
+  const int tf = d->precision == B200SHT_PREC_TF32 ? 2 : 0;
   float* spec_x = spec_x_saved ? spec_x_saved : ws.spec_in;
   rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc) rc = b200sht_legendre_analysis(f, ws.lat_in, spec_x, d->B, d->Cin, d->precision, stream);
   if (!rc && residual) {
     rc = b200sht_legendre_synthesis(v, spec_x, ws.lat_out, d->B, d->Cin, d->precision, stream);
-    if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0, stream);
+    if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0 | tf, stream);
   }
   if (!rc) rc = b200sht_mix_forward(f->lmax, f->mmax, d->op, spec_x, w, nullptr, ws.spec_out, d->B, d->G, d->Cin, d->Cout, d->precision, stream);
   if (!rc) rc = b200sht_legendre_synthesis(v, ws.spec_out, ws.lat_out, d->B, d->Cout, d->precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, y, d->dtype, d->B, d->Cout, bias, 0, stream);
+  if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, y, d->dtype, d->B, d->Cout, bias, 0 | tf, stream);
   return rc;
 }
 
@@ -449,7 +457,7 @@ int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v,
       }
     }
     if (!rc) rc = b200sht_legendre_synthesis(f, ws.spec_in, ws.lat_in, d->B, d->Cin, d->precision, stream);
-    if (!rc) rc = b200sht_fft_synthesis(f, ws.lat_in, gx, d->dtype, d->B, d->Cin, nullptr, 1, stream);
+    if (!rc) rc = b200sht_fft_synthesis(f, ws.lat_in, gx, d->dtype, d->B, d->Cin, nullptr, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   }
   return rc;
 }
@@ -480,6 +488,11 @@ int b200sht_spectral_conv_forward_host(const b200sht_plan* f, const b200sht_plan
     return B200SHT_ERR_CUDA;
   }
   return rc;
+}
+
+int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float row_scale, const float* in, float* out) {
+  B200_REQUIRE(in && out && N > 0 && mmax > 0, "debug_dft_host: bad argument");
+  return dft_host(N, mmax, direction, scale_mode & 1, &row_scale, in, out);
 }
 
 }  // extern "C"

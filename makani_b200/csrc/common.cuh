@@ -73,6 +73,7 @@ struct Plan {
   int sm_count;
   int umma_ok;          // tcgen05 path usable on this device
   void* umma_state;     // TMA descriptors etc. (owned by umma translation unit)
+  void* dft_state;      // tensor-core DFT tables (dft.cu); null when the grid is outside its range or tcgen05 is unavailable
 };
 
 }  // namespace b200sht

@@ -1,0 +1,691 @@
+// Longitude transform on the tensor cores (B200SHT_PREC_TF32): the truncated real DFT of every latitude row as
+//   radix-8 butterflies + twiddles on the CUDA cores  x  one class-independent [M2 x N2/2] DFT matrix on tcgen05 (kind::tf32).
+// Replaces the CUDA-core Stockham kernels of fft.cu for nlon = 8 * N2, N2 <= 190, mmax <= 256 (every shipped grid); see dft_math.cuh
+// for the factorisation.  Reference semantics: 2 pi * torch.fft.rfft(x, norm="forward")[..., :mmax] and torch.fft.irfft(Z, n=nlon,
+// norm="forward") inside torch_harmonics.RealSHT / InverseRealSHT (call sites makani/models/common/spectral_convolution.py:239,253).
+//
+// Why: the Stockham kernels were issue-bound on the CUDA cores (64.7 M warp instructions, 0.26-0.29 of HBM bandwidth):
+// a B200 has ~37 TFLOP/s of fp32 add/mul against 6.5 TB/s, and a 1440-point row is 34 kflop for 4.8 KB.  Here two of the three
+// radix stages (the 31 x 180 sub-transform, 86 % of the flops) run on the tensor pipe at TF32 and only one radix-8 stage stays on the
+// CUDA cores; no shared-memory exchange between stages is left.
+//
+// synthesis kernel (latspec -> rows):   TMEM lane = column j2 (<= N2/2, replicated when N2/2 < 64 so that all four SM sub-partitions
+//   work), accumulator columns = (class c, latitude k) of an 8-row tile.  A = E^T resident in shared memory (32 KB), B = the raw
+//   latspec tile [m2][(c, k)] streamed by TMA (16 KB per 8 rows), four accumulators S1..S4 (cos/sin x re/im), double buffered.
+//   Epilogue warps: tcgen05.ld -> V(j2), V(N2-j2) -> twiddle -> radix-8 -> scale/bias -> bf16; a warp stores 32 consecutive
+//   longitudes of one row per instruction.
+// analysis kernel (rows -> latspec):    producer warps load the eight samples x[N2 j1 + j2] of a column (lanes = consecutive j2),
+//   butterfly + twiddle them and write the even/odd combinations (Ye, Yo) as K-major TF32 operand tiles [(c, k)][j2] (128-byte
+//   swizzle, conflict-free row stores); B = E resident (<= 24 KB); D[(c,k)][m2] in TMEM; epilogue scales and writes latspec
+//   (64-byte runs along k).
+#include "umma_common.cuh"
+#include "dft_math.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace b200sht {
+
+int umma_available();   // umma.cu
+
+constexpr int kDftMaxHalf = 95;    // N2 / 2 <= 95: three 32-lane quadrants (synthesis) / three K-blocks (analysis)
+constexpr int kDftSynThreads = 512;
+constexpr int kDftSynStages = 8;   // 16 KB each
+constexpr int kDftAnaStages = 3;   // 64 KB each
+
+struct DftTables {
+  float* et;      // synthesis A: [2][128 rows = lane -> j2][32 m2]  (cos, sin), TF32-rounded
+  float* eb;      // analysis  B: [nkb][2][32 rows m2][32 j2 local]  (cos, sin), TF32-rounded
+  float2* tw;     // [8][N2]  exp(+2 pi i c j2 / nlon)
+  int N2, half, M2, qpr, nrep, nkb;
+};
+
+bool dft_shape_ok(int nlon, int mmax) {
+  if (nlon % 8 != 0) return false;
+  const int N2 = nlon / 8;
+  return N2 >= 2 && N2 / 2 <= kDftMaxHalf && (mmax + 7) / 8 <= 32 && mmax <= nlon / 2 + 1;
+}
+
+__global__ void dft_tables_kernel(float* et, float* eb, float2* tw, int N2, int half, int M2, int qpr, int nrep, int nkb, int nlon) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // E^T tiles: [2][128][32]
+  if (i < 2 * 128 * 32) {
+    const int m2 = i % 32, lane = (i / 32) % 128, p = i / (32 * 128);
+    const int rep = lane / (32 * qpr), j2 = lane - rep * 32 * qpr;
+    float v = 0.f;
+    if (rep < nrep && j2 <= half && m2 < M2) {
+      const long long t = ((long long)m2 * j2) % N2;
+      const double ang = 2.0 * M_PI * (double)t / (double)N2;
+      v = tf32_rn((float)(p == 0 ? cos(ang) : sin(ang)));
+    }
+    et[i] = v;
+  }
+  if (i < nkb * 2 * 32 * 32) {
+    const int jl = i % 32, m2 = (i / 32) % 32, p = (i / 1024) % 2, kb = i / 2048;
+    const int j2 = kb * 32 + jl;
+    float v = 0.f;
+    if (j2 <= half && m2 < M2) {
+      const long long t = ((long long)m2 * j2) % N2;
+      const double ang = 2.0 * M_PI * (double)t / (double)N2;
+      v = tf32_rn((float)(p == 0 ? cos(ang) : sin(ang)));
+    }
+    eb[i] = v;
+  }
+  if (i < 8 * N2) {
+    const int j2 = i % N2, c = i / N2;
+    const double ang = 2.0 * M_PI * (double)(c * j2) / (double)nlon;
+    tw[i] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+}
+
+int dft_plan_init(Plan* pl) {
+  pl->dft_state = nullptr;
+  if (!umma_available()) return -1;
+  if (!dft_shape_ok(pl->nlon, pl->mmax)) return -1;
+  DftTables* t = new DftTables();
+  t->N2 = pl->nlon / 8; t->half = t->N2 / 2; t->M2 = (pl->mmax + 7) / 8;
+  t->qpr = (t->half + 1 + 31) / 32;
+  t->nrep = t->qpr == 1 ? 4 : (t->qpr == 2 ? 2 : 1);
+  t->nkb = t->qpr;
+  t->et = nullptr; t->eb = nullptr; t->tw = nullptr;
+  const size_t neb = (size_t)t->nkb * 2 * 32 * 32;
+  cudaError_t e = cudaMalloc(&t->et, sizeof(float) * 2 * 128 * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&t->eb, sizeof(float) * neb);
+  if (e == cudaSuccess) e = cudaMalloc(&t->tw, sizeof(float2) * 8 * t->N2);
+  if (e == cudaSuccess) {
+    const int n = 8192 > 8 * t->N2 ? 8192 : 8 * t->N2;
+    dft_tables_kernel<<<(n + 255) / 256, 256>>>(t->et, t->eb, t->tw, t->N2, t->half, t->M2, t->qpr, t->nrep, t->nkb, pl->nlon);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw);
+    delete t;
+    return -1;
+  }
+  pl->dft_state = t;
+  return 0;
+}
+
+void dft_plan_destroy(Plan* pl) {
+  DftTables* t = static_cast<DftTables*>(pl->dft_state);
+  if (!t) return;
+  cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw);
+  delete t;
+  pl->dft_state = nullptr;
+}
+
+static bool dft_enabled() {
+  static const int on = [] { const char* e = getenv("B200SHT_DFT"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+bool dft_usable(const Plan* pl) { return pl->dft_state != nullptr && dft_enabled(); }
+
+// ------------------------------------------------------------------------------------------------ small PTX
+__device__ __forceinline__ pr tmem_ld2(uint32_t taddr) {
+  uint32_t a, b;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+  return make_pr(__uint_as_float(a), __uint_as_float(b));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <typename T> __device__ __forceinline__ void st_out(T* p, float v);
+template <> __device__ __forceinline__ void st_out<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ float ld_in(const T* p);
+template <> __device__ __forceinline__ float ld_in<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+// ================================================================================================ synthesis
+struct DftSynParams {
+  alignas(64) CUtensorMap tmZ;   // latspec as (k, c, m2, p, r), box (8, 4, 32, 1, 1): MN-major B operand, N = (c, k)
+  alignas(64) CUtensorMap tmE;   // E^T tiles (m2, 256 rows), box (32, 128): K-major A operand
+  const float* Z;
+  void* y;
+  const float2* tw;
+  const float* rowscale;
+  const float* bias;
+  int R, C, nlat, nlon, kp, mmax, N2, half, qpr, nrep, mode, ntiles, ktiles, has_nyq;
+  uint32_t idesc;
+};
+
+// shared memory: [A: cos 16 KB | sin 16 KB][B ring: kDftSynStages x 16 KB][tw table 8 x N2 float2][barriers]
+template <typename T>
+__global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const __grid_constant__ DftSynParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + 32768;
+  float2* tws = reinterpret_cast<float2*>(gbase + 32768 + kDftSynStages * 16384);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 32768 + kDftSynStages * 16384 + ((8 * p.N2 * 8 + 15) & ~15));
+  uint64_t* full = bars;
+  uint64_t* empty = full + kDftSynStages;
+  uint64_t* acc_full = empty + kDftSynStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* e_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, sub = warp >> 2;
+  const int subs = 4 / p.nrep;                                  // k pairs per replica
+  const bool is_tma = (warp == 15), is_mma = (warp == 11);
+  const bool is_epi = !is_tma && !is_mma && quad < p.qpr * p.nrep && sub < subs;
+  const int n_epi = p.qpr * p.nrep * subs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDftSynStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], n_epi); }
+    mbar_init(e_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.tmZ);
+    prefetch_tmap(&p.tmE);
+  }
+  for (int i = threadIdx.x; i < 8 * p.N2; i += blockDim.x) tws[i] = p.tw[i];
+  if (is_mma) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (is_tma) {
+    if (lane == 0) {
+      mbar_expect_tx(e_full, 32768);
+      tma_load_2d(sA, &p.tmE, e_full, 0, 0);
+      tma_load_2d(sA + 16384, &p.tmE, e_full, 0, 128);
+      int n = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+        const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 8;
+        const int s = n % kDftSynStages, it = n / kDftSynStages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        mbar_expect_tx(&full[s], 16384);
+        const uint32_t st = sB + s * 16384;
+        tma_load_5d(st, &p.tmZ, &full[s], k0, 0, 0, 0, r);
+        tma_load_5d(st + 4096, &p.tmZ, &full[s], k0, 4, 0, 0, r);
+        tma_load_5d(st + 8192, &p.tmZ, &full[s], k0, 0, 0, 1, r);
+        tma_load_5d(st + 12288, &p.tmZ, &full[s], k0, 4, 0, 1, r);
+      }
+    }
+    __syncwarp();
+  } else if (is_mma) {
+    if (lane == 0) {
+      mbar_wait(e_full, 0);
+      int n = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+        const int s = n % kDftSynStages, it = n / kDftSynStages;
+        const int buf = n & 1, use = n >> 1;
+        if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); }
+        mbar_wait(&full[s], it & 1);
+        tc_fence_after();
+        const uint32_t st = sB + s * 16384;
+        const uint32_t d = tmem + buf * 256;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t ac = desc_kmajor(sA, j), as = desc_kmajor(sA + 16384, j);
+          const uint64_t zr = desc_mnmajor(st, j, 4096), zi = desc_mnmajor(st + 8192, j, 4096);
+          const uint32_t acc = j > 0 ? 1u : 0u;
+          umma_tf32(d, ac, zr, p.idesc, acc);          // S1 = cos . Zr
+          umma_tf32(d + 64, as, zi, p.idesc, acc);     // S2 = sin . Zi
+          umma_tf32(d + 128, as, zr, p.idesc, acc);    // S3 = sin . Zr
+          umma_tf32(d + 192, ac, zi, p.idesc, acc);    // S4 = cos . Zi
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (is_epi) {
+    const int rep = quad / p.qpr;
+    const int j2 = 32 * (quad - rep * p.qpr) + lane;
+    const bool valid = j2 <= p.half;
+    const bool paired = valid && j2 != 0 && 2 * j2 != p.N2;
+    const int jp = p.N2 - j2;
+    const int kpi = rep * subs + sub;
+    const int N2 = p.N2;
+    T* const y = static_cast<T*>(p.y);
+    const float smul = p.mode == 0 ? 2.f : 1.f;
+    const int nyq_m = p.nlon / 2;
+    int n = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 8;
+      const int ka = k0 + 2 * kpi;
+      const int buf = n & 1, use = n >> 1;
+      // per-row output factors:  out = x * sc + off(parity)
+      float rsa = 1.f, rsb = 1.f, z0a = 0.f, z0b = 0.f, zna = 0.f, znb = 0.f;
+      if (p.mode == 1) {
+        const float2 rs = *reinterpret_cast<const float2*>(p.rowscale + ka);
+        rsa = rs.x; rsb = rs.y;
+      } else {
+        const float2 z0 = *reinterpret_cast<const float2*>(p.Z + (size_t)r * p.kp + ka);
+        z0a = z0.x; z0b = z0.y;
+        if (p.has_nyq) {
+          const float2 zn = *reinterpret_cast<const float2*>(p.Z + ((size_t)nyq_m * 2 * p.R + r) * p.kp + ka);
+          zna = zn.x; znb = zn.y;
+        }
+      }
+      const float bias = p.bias ? __ldg(p.bias + r % p.C) : 0.f;
+      const pr sc = make_pr(smul * rsa, smul * rsb);
+      const pr off_e = make_pr(bias - rsa * (z0a + zna), bias - rsb * (z0b + znb));   // even longitude j
+      const pr off_o = make_pr(bias - rsa * (z0a - zna), bias - rsb * (z0b - znb));   // odd longitude j
+      mbar_wait(&acc_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + 2 * kpi;
+      pr s1[8], s2[8], s3[8], s4[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        s1[c] = tmem_ld2(t0 + c * 8);
+        s2[c] = tmem_ld2(t0 + 64 + c * 8);
+        s3[c] = tmem_ld2(t0 + 128 + c * 8);
+        s4[c] = tmem_ld2(t0 + 192 + c * 8);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the accumulators are in registers: release the set
+      if (!valid) continue;
+      const bool oka = ka < p.nlat, okb = ka + 1 < p.nlat;
+      T* const rowa = y + ((size_t)r * p.nlat + (oka ? ka : 0)) * p.nlon;
+      T* const rowb = rowa + p.nlon;
+      float2 tw[8];
+#pragma unroll
+      for (int c = 1; c < 8; ++c) tw[c] = tws[c * N2 + j2];
+      {
+        pr vr[8], vi[8], x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { vr[c] = s1[c] - s2[c]; vi[c] = s3[c] + s4[c]; }
+        dft_syn_radix8<pr>(vr, vi, tw, x);
+#pragma unroll
+        for (int j1 = 0; j1 < 8; ++j1) {
+          const int j = N2 * j1 + j2;
+          const pr o = rfma(x[j1], sc, (j & 1) ? off_o : off_e);
+          if (oka) st_out<T>(rowa + j, o.v.x);
+          if (okb) st_out<T>(rowb + j, o.v.y);
+        }
+      }
+      if (paired) {
+        float2 tp[8];
+        dft_partner_twiddles(tw, tp);
+        pr vr[8], vi[8], x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { vr[c] = s1[c] + s2[c]; vi[c] = s4[c] - s3[c]; }
+        dft_syn_radix8<pr>(vr, vi, tp, x);
+#pragma unroll
+        for (int j1 = 0; j1 < 8; ++j1) {
+          const int j = N2 * j1 + jp;
+          const pr o = rfma(x[j1], sc, (j & 1) ? off_o : off_e);
+          if (oka) st_out<T>(rowa + j, o.v.x);
+          if (okb) st_out<T>(rowb + j, o.v.y);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_mma) tmem_dealloc(tmem, 512);
+}
+
+int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int mode, cudaStream_t st) {
+  const DftTables* t = static_cast<const DftTables*>(pl->dft_state);
+  B200_REQUIRE(t != nullptr, "dft_synthesis: plan has no DFT tables");
+  const int R = B * C;
+  DftSynParams p;
+  memset(&p, 0, sizeof(p));
+  p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias;
+  p.R = R; p.C = C; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
+  p.N2 = t->N2; p.half = t->half; p.qpr = t->qpr; p.nrep = t->nrep; p.mode = mode;
+  p.ktiles = pl->kp / 8; p.ntiles = R * p.ktiles;
+  p.has_nyq = (pl->mmax == pl->nlon / 2 + 1) ? 1 : 0;
+  p.idesc = make_idesc(64, 0, 1, 0);
+  // orders mmax .. 8 * M2 - 1 are read by the TMA boxes (class c, row m2 = M2 - 1): they must hold zeros.  The latspec buffers are
+  // sized for round_up(mmax, 8) planes (b200sht_latspec_elems); the pad planes are cleared here.
+  const size_t plane = (size_t)2 * R * pl->kp;
+  if (8 * t->M2 > pl->mmax)
+    B200_CHECK_CUDA(cudaMemsetAsync(const_cast<float*>(Z) + (size_t)pl->mmax * plane, 0, sizeof(float) * (size_t)(8 * t->M2 - pl->mmax) * plane, st));
+  {
+    const long long rk = (long long)R * pl->kp;
+    long long d[5] = {pl->kp, 8, t->M2, 2, R}, s[5] = {1, 2 * rk, 16 * rk, rk, pl->kp};
+    int bx[5] = {8, 4, 32, 1, 1};
+    int rc = make_tmap(&p.tmZ, Z, 5, d, s, bx, true);
+    if (rc) return rc;
+  }
+  {
+    long long d[2] = {32, 256}, s[2] = {1, 32};
+    int bx[2] = {32, 128};
+    int rc = make_tmap(&p.tmE, t->et, 2, d, s, bx);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + 32768 + (size_t)kDftSynStages * 16384 + ((8 * (size_t)t->N2 * 8 + 15) & ~(size_t)15) + (2 * kDftSynStages + 5) * 8 + 16;
+  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  const int ctas = p.ntiles < sms ? p.ntiles : sms;
+  if (dtype == B200SHT_BF16) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dft_synthesis_kernel<__nv_bfloat16><<<ctas, kDftSynThreads, smem, st>>>(p);
+  } else {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dft_synthesis_kernel<float><<<ctas, kDftSynThreads, smem, st>>>(p);
+  }
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ================================================================================================= analysis
+struct DftAnaParams {
+  alignas(64) CUtensorMap tmB;   // E tiles (32 j2 local, nkb * 64 rows), box (32, 32): K-major B operand
+  const void* x;
+  float* X;
+  const float2* tw;
+  const float* rowscale;
+  int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nslots;
+  uint32_t idesc, idesc_neg;
+};
+
+// warps: 0..3 epilogue (TMEM quadrant = warp), 4 MMA issuer (+ TMEM owner, loads the resident B), 5.. producers
+// shared memory: [B resident: nkb x (cos 4 KB | sin 4 KB)][A ring: kDftAnaStages x 4 planes x 16 KB][barriers]
+template <typename T>
+__global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sBm = base;                            // resident E
+  const uint32_t sAr = base + 3 * 8192;                 // A ring (1024-aligned: 24576)
+  uint8_t* gA = gbase + 3 * 8192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 3 * 8192 + kDftAnaStages * 65536);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kDftAnaStages;
+  uint64_t* acc_full = empty + kDftAnaStages;
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* b_full = acc_empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.nkb;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDftAnaStages; ++s) { mbar_init(&full[s], p.nslots); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)nkb * 8192);
+      for (int kb = 0; kb < nkb; ++kb) {
+        tma_load_2d(sBm + kb * 8192, &p.tmB, b_full, 0, kb * 64);
+        tma_load_2d(sBm + kb * 8192 + 4096, &p.tmB, b_full, 0, kb * 64 + 32);
+      }
+      mbar_wait(b_full, 0);
+      int n = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+        const int buf = n & 3, use = n >> 2;
+        if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * 64;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
+          mbar_wait(&full[s], it & 1);
+          tc_fence_after();
+          const uint32_t st = sAr + s * 65536;
+          const uint32_t bc = sBm + kb * 8192, bs = bc + 4096;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+            umma_tf32(d, desc_kmajor(st, j), desc_kmajor(bc, j), p.idesc, acc);                    // Xre  = Ye_r cos
+            umma_tf32(d, desc_kmajor(st + 49152, j), desc_kmajor(bs, j), p.idesc, 1u);            // Xre += Yo_i sin
+            umma_tf32(d + 32, desc_kmajor(st + 16384, j), desc_kmajor(bc, j), p.idesc, acc);      // Xim  = Ye_i cos
+            umma_tf32(d + 32, desc_kmajor(st + 32768, j), desc_kmajor(bs, j), p.idesc_neg, 1u);   // Xim -= Yo_r sin
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int c = 2 * warp + (lane >> 4), kr = lane & 15;
+    const size_t plane = (size_t)p.R * p.kp;
+    int n = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16;
+      const int k = k0 + kr;
+      const int buf = n & 3, use = n >> 2;
+      const bool kok = k < p.kp;
+      const float rs = (p.mode == 0) ? ((k < p.nlat) ? __ldg(p.rowscale + k) : 0.f) : 1.f;
+      mbar_wait(&acc_full[buf], use & 1);
+      tc_fence_after();
+      float vr[32], vi[32];
+      const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16) + buf * 64;
+      tmem_ld32_nowait(t0, vr);
+      tmem_ld32_nowait(t0 + 32, vi);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (!kok) continue;
+      float* xb = p.X + (size_t)r * p.kp + k;
+#pragma unroll
+      for (int m2 = 0; m2 < 32; ++m2) {
+        const int m = c + 8 * m2;
+        if (m >= p.mmax) break;
+        const float sc = (p.mode == 0) ? rs : ((m == 0 || 2 * m == p.nlon) ? 1.f : 2.f);
+        float a = vr[m2] * sc, b = vi[m2] * sc;
+        if (p.round_tf32) { a = tf32_rn(a); b = tf32_rn(b); }
+        float* dst = xb + (size_t)m * 2 * plane;
+        dst[0] = a;
+        dst[plane] = b;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- producers
+    const int pw = warp - 5;
+    const int kb = pw % nkb, slot = pw / nkb;
+    const int j2 = 32 * kb + lane;
+    const bool valid = j2 <= p.half;
+    const bool paired = valid && j2 != 0 && 2 * j2 != p.N2;
+    const int jp = p.N2 - j2;
+    const int N2 = p.N2;
+    float2 tw[8], tp[8];
+#pragma unroll
+    for (int c = 1; c < 8; ++c) tw[c] = valid ? p.tw[c * N2 + j2] : make_float2(1.f, 0.f);
+    tw[0] = make_float2(1.f, 0.f);
+    dft_partner_twiddles(tw, tp);
+    const T* const x = static_cast<const T*>(p.x);
+    // swizzled position of (row, column lane) in a K-major 128-byte-swizzle tile
+    int n = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16;
+      const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
+      if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+      float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
+      for (int kr = slot; kr < 16; kr += p.nslots) {
+        const int k = k0 + kr;
+        float er[8], ei[8], orr[8], oi[8];
+        if (valid && k < p.nlat) {
+          const T* row = x + ((size_t)r * p.nlat + k) * p.nlon;
+          float xa[8];
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) xa[j1] = ld_in<T>(row + N2 * j1 + j2);
+          dft_ana_radix8<float>(xa, tw, er, ei);
+          if (paired) {
+            float xb[8], br[8], bi[8];
+#pragma unroll
+            for (int j1 = 0; j1 < 8; ++j1) xb[j1] = ld_in<T>(row + N2 * j1 + jp);
+            dft_ana_radix8<float>(xb, tp, br, bi);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              orr[c] = er[c] - br[c]; oi[c] = ei[c] - bi[c];
+              er[c] += br[c]; ei[c] += bi[c];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { orr[c] = 0.f; oi[c] = 0.f; }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { er[c] = 0.f; ei[c] = 0.f; orr[c] = 0.f; oi[c] = 0.f; }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int row = c * 16 + kr;
+          const int off = row * 32 + ((((lane >> 2) ^ (row & 7)) << 2) | (lane & 3));
+          stg[off] = tf32_rn(er[c]);
+          stg[4096 + off] = tf32_rn(ei[c]);
+          stg[8192 + off] = tf32_rn(orr[c]);
+          stg[12288 + off] = tf32_rn(oi[c]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int mode, int round_tf32, cudaStream_t st) {
+  const DftTables* t = static_cast<const DftTables*>(pl->dft_state);
+  B200_REQUIRE(t != nullptr, "dft_analysis: plan has no DFT tables");
+  const int R = B * C;
+  DftAnaParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale;
+  p.R = R; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
+  p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
+  p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
+  const int pwarps = (t->nkb == 3) ? 12 : 8;
+  p.nslots = pwarps / t->nkb;
+  p.idesc = make_idesc(32, 0, 0, 0);
+  p.idesc_neg = make_idesc(32, 0, 0, 1);
+  {
+    long long d[2] = {32, (long long)t->nkb * 64}, s[2] = {1, 32};
+    int bx[2] = {32, 32};
+    int rc = make_tmap(&p.tmB, t->eb, 2, d, s, bx);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + (2 * kDftAnaStages + 9) * 8 + 16;
+  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  const int ctas = p.ntiles < sms ? p.ntiles : sms;
+  const int threads = 32 * (5 + pwarps);
+  if (dtype == B200SHT_BF16) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dft_analysis_kernel<__nv_bfloat16><<<ctas, threads, smem, st>>>(p);
+  } else {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dft_analysis_kernel<float><<<ctas, threads, smem, st>>>(p);
+  }
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// ============================================================================================ host emulation
+// The same factorisation and the same __host__ __device__ radix-8 code as the kernels, with the tensor-core sums done in double
+// precision on the host: unit-tests the index maps, twiddles and butterflies without a GPU (b200sht_debug_dft_host).
+int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out) {
+  if (!dft_shape_ok(N, mmax)) { set_error("debug_dft_host: unsupported (nlon=%d, mmax=%d)", N, mmax); return B200SHT_ERR_UNSUPPORTED; }
+  const int N2 = N / 8, half = N2 / 2, M2 = (mmax + 7) / 8;
+  const float rs = rowscale ? rowscale[0] : 1.f;
+  auto twid = [&](int j, float2* tw) {
+    for (int c = 0; c < 8; ++c) {
+      const double a = 2.0 * M_PI * (double)(c * j) / (double)N;
+      tw[c] = make_float2((float)cos(a), (float)sin(a));
+    }
+  };
+  if (direction == 1) {
+    // in: float[2 * mmax] interleaved (re, im) -> out: float[N]
+    std::vector<double> zr(8 * M2, 0.0), zi(8 * M2, 0.0);
+    for (int m = 0; m < mmax; ++m) { zr[m] = in[2 * m]; zi[m] = in[2 * m + 1]; }
+    const bool has_nyq = (mmax == N / 2 + 1);
+    for (int j2 = 0; j2 <= half; ++j2) {
+      float s1[8], s2[8], s3[8], s4[8];
+      for (int c = 0; c < 8; ++c) {
+        double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        for (int m2 = 0; m2 < M2; ++m2) {
+          const double b = 2.0 * M_PI * (double)(((long long)m2 * j2) % N2) / (double)N2;
+          a1 += cos(b) * zr[c + 8 * m2]; a2 += sin(b) * zi[c + 8 * m2]; a3 += sin(b) * zr[c + 8 * m2]; a4 += cos(b) * zi[c + 8 * m2];
+        }
+        s1[c] = (float)a1; s2[c] = (float)a2; s3[c] = (float)a3; s4[c] = (float)a4;
+      }
+      float2 tw[8], tp[8];
+      twid(j2, tw);
+      dft_partner_twiddles(tw, tp);
+      for (int side = 0; side < 2; ++side) {
+        if (side == 1 && (j2 == 0 || 2 * j2 == N2)) continue;
+        const int jj = side ? N2 - j2 : j2;
+        float vr[8], vi[8], x[8];
+        for (int c = 0; c < 8; ++c) {
+          vr[c] = side ? s1[c] + s2[c] : s1[c] - s2[c];
+          vi[c] = side ? s4[c] - s3[c] : s3[c] + s4[c];
+        }
+        dft_syn_radix8<float>(vr, vi, side ? tp : tw, x);
+        for (int j1 = 0; j1 < 8; ++j1) {
+          const int j = N2 * j1 + jj;
+          float v = x[j1];
+          if (mode == 0) {
+            v = 2.f * v - (float)zr[0];
+            if (has_nyq) v -= (float)zr[N / 2] * ((j & 1) ? -1.f : 1.f);
+          } else {
+            v *= rs;
+          }
+          out[j] = v;
+        }
+      }
+    }
+    return 0;
+  }
+  // analysis: in float[N] -> out float[2 * mmax]
+  std::vector<double> dre(8 * M2, 0.0), dim(8 * M2, 0.0);
+  for (int j2 = 0; j2 <= half; ++j2) {
+    float2 tw[8], tp[8];
+    twid(j2, tw);
+    dft_partner_twiddles(tw, tp);
+    float xa[8], er[8], ei[8], orr[8], oi[8];
+    for (int j1 = 0; j1 < 8; ++j1) xa[j1] = in[N2 * j1 + j2];
+    dft_ana_radix8<float>(xa, tw, er, ei);
+    const bool paired = (j2 != 0 && 2 * j2 != N2);
+    if (paired) {
+      float xb[8], br[8], bi[8];
+      for (int j1 = 0; j1 < 8; ++j1) xb[j1] = in[N2 * j1 + N2 - j2];
+      dft_ana_radix8<float>(xb, tp, br, bi);
+      for (int c = 0; c < 8; ++c) { orr[c] = er[c] - br[c]; oi[c] = ei[c] - bi[c]; er[c] += br[c]; ei[c] += bi[c]; }
+    } else {
+      for (int c = 0; c < 8; ++c) { orr[c] = 0.f; oi[c] = 0.f; }
+    }
+    for (int c = 0; c < 8; ++c)
+      for (int m2 = 0; m2 < M2; ++m2) {
+        const double b = 2.0 * M_PI * (double)(((long long)m2 * j2) % N2) / (double)N2;
+        dre[c + 8 * m2] += cos(b) * er[c] + sin(b) * oi[c];
+        dim[c + 8 * m2] += cos(b) * ei[c] - sin(b) * orr[c];
+      }
+  }
+  for (int m = 0; m < mmax; ++m) {
+    const double sc = mode == 0 ? (double)rs : ((m == 0 || 2 * m == N) ? 1.0 : 2.0);
+    out[2 * m] = (float)(dre[m] * sc);
+    out[2 * m + 1] = (float)(dim[m] * sc);
+  }
+  return 0;
+}
+
+}  // namespace b200sht

@@ -75,6 +75,11 @@ class Plan:
         self.nlat, self.nlon, self.lmax, self.mmax, self.m_offset = nlat, nlon, lmax, mmax, m_offset
         self.kp = int(lib.b200sht_plan_query(handle, 4))
         self.umma_ok = bool(lib.b200sht_plan_query(handle, 6))
+        self.dft_ok = bool(lib.b200sht_plan_query(handle, 8))
+
+    def query(self, what):
+        """b200sht_plan_query: 0 nlat, 1 nlon, 2 lmax, 3 mmax, 4 kp, 5 table bytes, 6 tcgen05 available, 7 m_offset, 8 tensor-core DFT available."""
+        return int(_lib.load().b200sht_plan_query(self.handle, what))
 
     @classmethod
     def create_ex(cls, nlat, nlon, lmax, mmax, m_offset, flags, cost, quad_w, csphase, device):
@@ -160,7 +165,7 @@ class _AnalysisPacked(torch.autograd.Function):
         gx = torch.empty(ctx.shape, dtype=ctx.dtype, device=dev)
         st = _stream(dev)
         _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(gspec), _ptr(lat), B, C, ctx.precision, st)
-        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(gx), _dtype_code(ctx.dtype), B, C, _VP(0), 1, st)
+        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(gx), _dtype_code(ctx.dtype), B, C, _VP(0), 1 | (2 if ctx.precision == _lib.PREC_TF32 else 0), st)
         return gx, None, None
 
 
@@ -178,7 +183,7 @@ class _SynthesisPacked(torch.autograd.Function):
         if bias is not None:
             b32 = bias.detach().reshape(-1).to(torch.float32).contiguous()
         _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(spec), _ptr(lat), B, C, precision, st)
-        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), _dtype_code(dtype), B, C, _ptr(b32), 0, st)
+        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), _dtype_code(dtype), B, C, _ptr(b32), 0 | (2 if precision == _lib.PREC_TF32 else 0), st)
         ctx.plan, ctx.precision, ctx.B, ctx.C = plan, precision, B, C
         ctx.has_bias = bias is not None
         ctx.bias_shape = tuple(bias.shape) if bias is not None else None
