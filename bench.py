@@ -463,17 +463,18 @@ def run_gpu_arm(args):
         gx_dev = torch.empty_like(x_dev)
         dt = _dtype_code(act_dtype)
         VP0 = mb.sht._VP(0)
+        tfb = 2 if prec == _lib.PREC_TF32 else 0   # TF32 precision bit of the longitude-transform entry points (tensor-core DFT)
         calls = {
-            "fft_analysis_in": lambda: _lib.call("b200sht_fft_analysis", plan_f.handle, _ptr(x_dev), dt, B, C, _ptr(lat_i), 0, st),
+            "fft_analysis_in": lambda: _lib.call("b200sht_fft_analysis", plan_f.handle, _ptr(x_dev), dt, B, C, _ptr(lat_i), 0 | tfb, st),
             "legendre_analysis_in": lambda: _lib.call("b200sht_legendre_analysis", plan_f.handle, _ptr(lat_i), _ptr(sp_a), B, C, prec, st),
             "mix_forward": lambda: _lib.call("b200sht_mix_forward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), VP0, _ptr(sp_b), B, 1, C, C, prec, st),
             "legendre_synthesis_out": lambda: _lib.call("b200sht_legendre_synthesis", plan_i.handle, _ptr(sp_b), _ptr(lat_o), B, C, prec, st),
-            "fft_synthesis_out": lambda: _lib.call("b200sht_fft_synthesis", plan_i.handle, _ptr(lat_o), _ptr(y_dev), dt, B, C, VP0, 0, st),
-            "fft_analysis_out": lambda: _lib.call("b200sht_fft_analysis", plan_i.handle, _ptr(gy), dt, B, C, _ptr(lat_o), 1, st),
+            "fft_synthesis_out": lambda: _lib.call("b200sht_fft_synthesis", plan_i.handle, _ptr(lat_o), _ptr(y_dev), dt, B, C, VP0, 0 | tfb, st),
+            "fft_analysis_out": lambda: _lib.call("b200sht_fft_analysis", plan_i.handle, _ptr(gy), dt, B, C, _ptr(lat_o), 1 | tfb, st),
             "legendre_analysis_out": lambda: _lib.call("b200sht_legendre_analysis", plan_i.handle, _ptr(lat_o), _ptr(sp_b), B, C, prec, st),
             "mix_backward": lambda: _lib.call("b200sht_mix_backward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), _ptr(sp_b), _ptr(sp_c), _ptr(gwpk), VP0, B, 1, C, C, prec, st),
             "legendre_synthesis_in": lambda: _lib.call("b200sht_legendre_synthesis", plan_f.handle, _ptr(sp_c), _ptr(lat_i), B, C, prec, st),
-            "fft_synthesis_in": lambda: _lib.call("b200sht_fft_synthesis", plan_f.handle, _ptr(lat_i), _ptr(gx_dev), dt, B, C, VP0, 1, st),
+            "fft_synthesis_in": lambda: _lib.call("b200sht_fft_synthesis", plan_f.handle, _ptr(lat_i), _ptr(gx_dev), dt, B, C, VP0, 1 | tfb, st),
         }
         sb = stage_bytes(wl, act_bytes)
         for name, fn in calls.items():
