@@ -144,6 +144,38 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
 template <typename T> __device__ __forceinline__ void st_out(T* p, float v);
 template <> __device__ __forceinline__ void st_out<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+// raw sample bits of the next item (converted when consumed): float bits, or the bf16 pattern in the low half
+template <typename T> __device__ __forceinline__ uint32_t ld_raw(const T* p);
+template <> __device__ __forceinline__ uint32_t ld_raw<float>(const float* p) { return __float_as_uint(__ldg(p)); }
+template <> __device__ __forceinline__ uint32_t ld_raw<__nv_bfloat16>(const __nv_bfloat16* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
+
+// How the CUDA-core producers turn an fp32 value into a kind::tf32 operand (the MMA truncates the 13 low mantissa bits):
+//   0  cvt.rna.tf32.f32                 3 instructions on sm_100a (FSETP + IADD + LOP3)
+//   1  (bits + 0x1000) & ~0x1fff        2 instructions, same result for finite values
+//   2  bias-compensated truncation      0 instructions: the value is pre-scaled by (1 + 2^-10 / 3) -- folded into the twiddle
+//      factors -- so that the hardware truncation error x f - delta, delta ~ U[0, ulp), has zero mean over a binade; its rms is
+//      0.304 ulp against 0.289 ulp for round-to-nearest, and TF32-exact inputs stay exact (x f < ulp / 3).
+#ifndef B200_DFT_TF32_MODE
+#define B200_DFT_TF32_MODE 2
+#endif
+constexpr float kTruncComp = 1.0f + 0.0009765625f / 3.0f;
+__device__ __forceinline__ float tf32_operand(float v) {
+#if B200_DFT_TF32_MODE == 0
+  return tf32_rn(v);
+#elif B200_DFT_TF32_MODE == 1
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+#else
+  return v;   // already scaled through the twiddles
+#endif
+}
+__device__ __forceinline__ float tf32_operand_unscaled(float v) {   // class 0 carries no twiddle
+#if B200_DFT_TF32_MODE == 2
+  return v * kTruncComp;
+#else
+  return tf32_operand(v);
+#endif
+}
+
 template <typename T> __device__ __forceinline__ float ld_in(const T* p);
 template <> __device__ __forceinline__ float ld_in<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfloat16* p) {
@@ -396,7 +428,7 @@ struct DftAnaParams {
 // warps: 0..3 epilogue (TMEM quadrant = warp), 4 MMA issuer (+ TMEM owner, loads the resident B), 5.. producers
 // shared memory: [B resident: nkb x (cos 4 KB | sin 4 KB)][A ring: kDftAnaStages x 4 planes x 16 KB][barriers]
 template <typename T>
-__global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
+__global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -498,6 +530,12 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     }
   } else {
     // ------------------------------------------------------------------------------------------- producers
+    // Warp = (K-block kb, slot): lanes are 32 consecutive columns j2 of K-block kb; the warp walks the rows slot, slot + nslots, ...
+    // of every tile.  Per row ("item") a lane loads its column and the partner column N2 - j2 (8 samples each, 64-byte runs per warp
+    // instruction), runs both radix-8 butterflies + twiddles and stores Ye = Y'(j2) + Y'(N2-j2), Yo = Y'(j2) - Y'(N2-j2) for the
+    // 8 classes into the four K-major operand planes (one 128-byte row per warp store: conflict free).
+    // Latency: the samples of the NEXT item are in flight (registers) while the current one is computed, and the rows of the tile
+    // after next are pulled into L2 by one prefetch per thread.  Lanes beyond N2/2 and rows beyond nlat carry zeros.
     const int pw = warp - 5;
     const int kb = pw % nkb, slot = pw / nkb;
     const int j2 = 32 * kb + lane;
@@ -505,55 +543,88 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     const bool paired = valid && j2 != 0 && 2 * j2 != p.N2;
     const int jp = p.N2 - j2;
     const int N2 = p.N2;
+    const int ipt = 16 / p.nslots;                 // items of this warp per tile (2 or 4)
+    const int nprod = (int)(blockDim.x >> 5) - 5;  // producer warps
     float2 tw[8], tp[8];
 #pragma unroll
     for (int c = 1; c < 8; ++c) tw[c] = valid ? p.tw[c * N2 + j2] : make_float2(1.f, 0.f);
     tw[0] = make_float2(1.f, 0.f);
     dft_partner_twiddles(tw, tp);
+#if B200_DFT_TF32_MODE == 2
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {
+      tw[c].x *= kTruncComp; tw[c].y *= kTruncComp;
+      tp[c].x *= kTruncComp; tp[c].y *= kTruncComp;
+    }
+#endif
     const T* const x = static_cast<const T*>(p.x);
-    // swizzled position of (row, column lane) in a K-major 128-byte-swizzle tile
+    constexpr bool kBf16 = (sizeof(T) == 2);
+    auto load_item = [&](uint32_t* raw, int n, int i) {
+      const int ti = blockIdx.x + n * gridDim.x;
+      if (ti >= p.ntiles) return;
+      const int r = ti / p.ktiles, k = (ti - r * p.ktiles) * 16 + slot + i * p.nslots;
+      if (valid && k < p.nlat) {
+        const T* row = x + ((size_t)r * p.nlat + k) * p.nlon;
+#pragma unroll
+        for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(row + N2 * j1 + j2);
+        if (paired) {
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(row + N2 * j1 + jp);
+        } else {
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = 0u;
+        }
+      } else {
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) raw[j1] = 0u;
+      }
+    };
+    auto compute_store = [&](const uint32_t* raw, float* stg, int kr) {
+      float xa[8], xb[8], er[8], ei[8], br[8], bi[8];
+#pragma unroll
+      for (int j1 = 0; j1 < 8; ++j1) {
+        xa[j1] = __uint_as_float(kBf16 ? raw[j1] << 16 : raw[j1]);
+        xb[j1] = __uint_as_float(kBf16 ? raw[8 + j1] << 16 : raw[8 + j1]);
+      }
+      dft_ana_radix8<float>(xa, tw, er, ei);
+      dft_ana_radix8<float>(xb, tp, br, bi);
+      // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8)
+      float* const dst = stg + kr * 32 + ((((lane >> 2) ^ (kr & 7)) << 2) | (lane & 3));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float ye_r = er[c] + br[c], yo_r = er[c] - br[c];
+        float ye_i = ei[c] + bi[c], yo_i = ei[c] - bi[c];
+        if (c == 0) { ye_r = tf32_operand_unscaled(ye_r); yo_r = tf32_operand_unscaled(yo_r); ye_i = 0.f; yo_i = 0.f; }
+        else { ye_r = tf32_operand(ye_r); yo_r = tf32_operand(yo_r); ye_i = tf32_operand(ye_i); yo_i = tf32_operand(yo_i); }
+        dst[c * 512] = ye_r;
+        dst[4096 + c * 512] = ye_i;
+        dst[8192 + c * 512] = yo_r;
+        dst[12288 + c * 512] = yo_i;
+      }
+    };
+    uint32_t rawA[16], rawB[16];
+    load_item(rawA, 0, 0);
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16;
+      {  // L2 prefetch of the tile after next (its samples are first touched ~2 tile times from now)
+        const int t2 = ti + 2 * gridDim.x;
+        if (t2 < p.ntiles) {
+          const int r2 = t2 / p.ktiles, k2 = (t2 - r2 * p.ktiles) * 16;
+          const int rows = p.nlat - k2 < 16 ? p.nlat - k2 : 16;
+          const char* b2 = reinterpret_cast<const char*>(x + ((size_t)r2 * p.nlat + k2) * p.nlon);
+          const int lines = (int)(((size_t)rows * p.nlon * sizeof(T) + 127) >> 7);
+          for (int l = pw * 32 + lane; l < lines; l += nprod * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)l * 128));
+        }
+      }
       const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
       if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
       float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
-      for (int kr = slot; kr < 16; kr += p.nslots) {
-        const int k = k0 + kr;
-        float er[8], ei[8], orr[8], oi[8];
-        if (valid && k < p.nlat) {
-          const T* row = x + ((size_t)r * p.nlat + k) * p.nlon;
-          float xa[8];
-#pragma unroll
-          for (int j1 = 0; j1 < 8; ++j1) xa[j1] = ld_in<T>(row + N2 * j1 + j2);
-          dft_ana_radix8<float>(xa, tw, er, ei);
-          if (paired) {
-            float xb[8], br[8], bi[8];
-#pragma unroll
-            for (int j1 = 0; j1 < 8; ++j1) xb[j1] = ld_in<T>(row + N2 * j1 + jp);
-            dft_ana_radix8<float>(xb, tp, br, bi);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              orr[c] = er[c] - br[c]; oi[c] = ei[c] - bi[c];
-              er[c] += br[c]; ei[c] += bi[c];
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { orr[c] = 0.f; oi[c] = 0.f; }
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { er[c] = 0.f; ei[c] = 0.f; orr[c] = 0.f; oi[c] = 0.f; }
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int row = c * 16 + kr;
-          const int off = row * 32 + ((((lane >> 2) ^ (row & 7)) << 2) | (lane & 3));
-          stg[off] = tf32_rn(er[c]);
-          stg[4096 + off] = tf32_rn(ei[c]);
-          stg[8192 + off] = tf32_rn(orr[c]);
-          stg[12288 + off] = tf32_rn(oi[c]);
-        }
+      for (int i = 0; i < ipt; i += 2) {
+        load_item(rawB, n, i + 1);
+        compute_store(rawA, stg, slot + i * p.nslots);
+        if (i + 2 < ipt) load_item(rawA, n, i + 2);
+        else load_item(rawA, n + 1, 0);
+        compute_store(rawB, stg, slot + (i + 1) * p.nslots);
       }
       fence_proxy_async();
       __syncwarp();

@@ -28,14 +28,32 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return done;
 }
-// bounded wait: a lost arrival traps (kernel error) instead of hanging the GPU
+// try_wait with a suspend-time hint: the warp sleeps in hardware (no issue slots) until the phase completes or ~`ns` elapse
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return done;
+}
+// bounded wait: a lost arrival traps (kernel error) instead of hanging the GPU.  The wall-clock check runs once per 256 wake-ups: the
+// polling loop of the first version (clock64 + compare every iteration) cost the CUDA-core warps of dft.cu a third of their issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("b200sht umma: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 255u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000LL) {
+        printf("b200sht: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+        __trap();
+      }
     }
   }
 }

@@ -310,7 +310,7 @@ class _ComplexReLUPacked(torch.autograd.Function):
         mode, slope, L, M, B, C, bshape = ctx.meta
         gy = gy.contiguous()
         gx = torch.empty_like(spec)
-        need_b = bshape is not None and ctx.needs_input_grad[1] and mode == 2
+        need_b = bshape is not None and ctx.needs_input_grad[1] and (mode & 0xFF) == 2
         gb = torch.empty(C, dtype=torch.float32, device=gy.device) if need_b else None
         _lib.call("b200sht_complex_relu_backward", L, M, mode, _ptr(spec), _ptr(b), float(slope), _ptr(gy), _ptr(gx), _ptr(gb), B, C,
                   _stream(gy.device))
@@ -341,11 +341,12 @@ class ComplexReLU(nn.Module):
             self.bias = 0
         self.negative_slope = negative_slope
 
-    def forward_packed(self, spec, L, M, B, C):
+    def forward_packed(self, spec, L, M, B, C, dense=False):
         if self.mode not in _RELU_MODES:
             raise NotImplementedError
         bias = self.bias if isinstance(self.bias, torch.Tensor) else None
-        return _ComplexReLUPacked.apply(spec, bias, _RELU_MODES[self.mode], self.negative_slope, L, M, B, C)
+        mode = _RELU_MODES[self.mode] | (_lib.DENSE_FLAG if dense else 0)
+        return _ComplexReLUPacked.apply(spec, bias, mode, self.negative_slope, L, M, B, C)
 
     def forward(self, z):
         if self.mode not in _RELU_MODES:
@@ -402,20 +403,31 @@ class SpectralAttention(nn.Module):
             scale = math.sqrt(gain / float(in_channels))
             self.wout = nn.Parameter(scale * torch.randn(self.modes_lat, hidden, out_channels, dtype=torch.complex64))
         self.activations = nn.ModuleList([ComplexReLU(mode=complex_activation, bias_shape=(hidden, 1, 1), scale=scale) for _ in range(spectral_layers)])
-        if drop_rate > 0.0:
-            raise NotImplementedError("dropout on complex spectra is not supported (the reference path raises as well)")
-        self.drop = nn.Identity()
+        # the reference builds nn.Dropout here (spectral_convolution.py:432); dropout on packed spectra is not implemented, so the
+        # constructor accepts drop_rate (configs load unchanged) and forward() raises when it would actually drop (training, p > 0)
+        self.drop_rate = float(drop_rate)
+        self.drop = nn.Dropout(drop_rate) if drop_rate > 0.0 else nn.Identity()
         self._caches = [PackedWeightCache() for _ in range(spectral_layers + 1)]
+        # l / m-sharded spectra (Distributed* transforms of the h x w path): the packed buffers hold the LOCAL modes, every (l, m) stored
+        self.modes_lat_local = getattr(inverse_transform, "lmax_local", self.modes_lat)
+        self.modes_lon_local = getattr(inverse_transform, "mmax_local", self.modes_lon)
+        self._dense = _lib.DENSE_FLAG if getattr(inverse_transform, "packed_dense", False) else 0
+        if operator_type == "l-dependant" and self.modes_lat_local != self.modes_lat:
+            raise ValueError("SpectralAttention(operator_type='l-dependant') with an l-sharded transform (h_parallel_size > 1) is not supported: "
+                             "its weights are indexed by the global degree")
 
     def _mlp_packed(self, h, B):
-        L, M = self.modes_lat, self.modes_lon
+        if self.training and self.drop_rate > 0.0:
+            raise NotImplementedError("SpectralAttention: dropout on complex spectra (drop_rate > 0 in training) is not implemented")
+        L, M = self.modes_lat_local, self.modes_lon_local
+        op = self._op | self._dense
         cin = self.in_channels
         for i in range(self.spectral_layers):
             cb = self.b[i] if hasattr(self, "b") else None
-            h = mix_packed(h, self.w[i], self._op, L, M, B, 1, cin, self.hidden_size, self.precision, cbias=cb, cache=self._caches[i])
-            h = self.activations[i].forward_packed(h, L, M, B, self.hidden_size)
+            h = mix_packed(h, self.w[i], op, L, M, B, 1, cin, self.hidden_size, self.precision, cbias=cb, cache=self._caches[i])
+            h = self.activations[i].forward_packed(h, L, M, B, self.hidden_size, dense=bool(self._dense))
             cin = self.hidden_size
-        return mix_packed(h, self.wout, self._op, L, M, B, 1, cin, self.out_channels, self.precision, cache=self._caches[-1])
+        return mix_packed(h, self.wout, op, L, M, B, 1, cin, self.out_channels, self.precision, cache=self._caches[-1])
 
     def forward_mlp(self, x):
         """complex (B, Cin, L, M) -> complex (B, Cout, L, M)."""

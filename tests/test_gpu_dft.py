@@ -25,7 +25,7 @@ CASES = [
     (240, 480, 241, 5, torch.bfloat16),
     (45, 360, 100, 2, torch.bfloat16),     # N2 = 45 (odd)
     (181, 720, 121, 3, torch.float32),     # N2 = 90: two lane quadrants
-    (7, 1520, 256, 2, torch.float32),      # largest supported length
+    (7, 1512, 256, 2, torch.float32),      # largest supported length class (N2 = 189, odd)
     (19, 16, 9, 3, torch.float32),         # smallest
 ]
 
