@@ -400,7 +400,7 @@ def run_gpu_arm(args):
 
     # kernel launches of OUR library inside one step (counted by the ctypes call wrapper)
     counter = {"n": 0}
-    kernels_per_call = {"b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1,
+    kernels_per_call = {"b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1, "b200sht_legendre_synthesis_tiled": 1,
                         "b200sht_mix_forward": 1, "b200sht_mix_backward": 2, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
                         "b200sht_bias_grad": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1,
                         # one-call entry points: fft + legendre + mix + legendre + fft / fft + legendre + dgrad + wgrad + legendre + fft
@@ -464,17 +464,26 @@ def run_gpu_arm(args):
         dt = _dtype_code(act_dtype)
         VP0 = mb.sht._VP(0)
         tfb = 2 if prec == _lib.PREC_TF32 else 0   # TF32 precision bit of the longitude-transform entry points (tensor-core DFT)
+
+        def syn_bit(plan):   # tiled latspec + tensor-core DFT when the plan has it (what SpectralConv's one-call path does)
+            return 2 if (tfb and plan.dft_ok) else 0
+
+        def leg_syn(plan, sp, lat):
+            if syn_bit(plan):
+                return _lib.call("b200sht_legendre_synthesis_tiled", plan.handle, _ptr(sp), _ptr(lat), B, C, st)
+            return _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(sp), _ptr(lat), B, C, prec, st)
+
         calls = {
             "fft_analysis_in": lambda: _lib.call("b200sht_fft_analysis", plan_f.handle, _ptr(x_dev), dt, B, C, _ptr(lat_i), 0 | tfb, st),
             "legendre_analysis_in": lambda: _lib.call("b200sht_legendre_analysis", plan_f.handle, _ptr(lat_i), _ptr(sp_a), B, C, prec, st),
             "mix_forward": lambda: _lib.call("b200sht_mix_forward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), VP0, _ptr(sp_b), B, 1, C, C, prec, st),
-            "legendre_synthesis_out": lambda: _lib.call("b200sht_legendre_synthesis", plan_i.handle, _ptr(sp_b), _ptr(lat_o), B, C, prec, st),
-            "fft_synthesis_out": lambda: _lib.call("b200sht_fft_synthesis", plan_i.handle, _ptr(lat_o), _ptr(y_dev), dt, B, C, VP0, 0 | tfb, st),
+            "legendre_synthesis_out": lambda: leg_syn(plan_i, sp_b, lat_o),
+            "fft_synthesis_out": lambda: _lib.call("b200sht_fft_synthesis", plan_i.handle, _ptr(lat_o), _ptr(y_dev), dt, B, C, VP0, 0 | syn_bit(plan_i), st),
             "fft_analysis_out": lambda: _lib.call("b200sht_fft_analysis", plan_i.handle, _ptr(gy), dt, B, C, _ptr(lat_o), 1 | tfb, st),
             "legendre_analysis_out": lambda: _lib.call("b200sht_legendre_analysis", plan_i.handle, _ptr(lat_o), _ptr(sp_b), B, C, prec, st),
             "mix_backward": lambda: _lib.call("b200sht_mix_backward", L, M, _lib.OP_DHCONV, _ptr(sp_a), _ptr(wpk), _ptr(sp_b), _ptr(sp_c), _ptr(gwpk), VP0, B, 1, C, C, prec, st),
-            "legendre_synthesis_in": lambda: _lib.call("b200sht_legendre_synthesis", plan_f.handle, _ptr(sp_c), _ptr(lat_i), B, C, prec, st),
-            "fft_synthesis_in": lambda: _lib.call("b200sht_fft_synthesis", plan_f.handle, _ptr(lat_i), _ptr(gx_dev), dt, B, C, VP0, 1 | tfb, st),
+            "legendre_synthesis_in": lambda: leg_syn(plan_f, sp_c, lat_i),
+            "fft_synthesis_in": lambda: _lib.call("b200sht_fft_synthesis", plan_f.handle, _ptr(lat_i), _ptr(gx_dev), dt, B, C, VP0, 1 | syn_bit(plan_f), st),
         }
         sb = stage_bytes(wl, act_bytes)
         for name, fn in calls.items():

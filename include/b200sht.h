@@ -110,9 +110,9 @@ int b200sht_fft_analysis(const b200sht_plan* plan, const void* x, int dtype, int
 /* Longitude synthesis: truncated half spectrum -> real rows (+ optional per-channel bias, cast to dtype).
  * scale_mode 0: irfft(norm="forward") semantics (imaginary part of m=0 / Nyquist ignored)
  * scale_mode 1: adjoint of the scale_mode-0 analysis (row_scale = quad_w[k] 2 pi/nlon, modes m>0 halved)
- * scale_mode | 2: TF32 precision (tensor-core DFT where the grid allows, see above).  That path reads the orders in residue classes
- *                 modulo 8, so `latspec` must have room for round_up(mmax, 8) orders (b200sht_latspec_elems does) and the call
- *                 CLEARS the padding orders mmax .. round_up(mmax, 8) - 1 of `latspec` (the only write to an input buffer in the API). */
+ * scale_mode | 2: `latspec` is in the TILED layout written by b200sht_legendre_synthesis_tiled and the transform runs on the tensor
+ *                 cores (TF32; radix-8 butterflies on the CUDA cores x a [mmax/8 x nlon/16] DFT matrix as a kind::tf32 GEMM, csrc/dft.cu).
+ *                 Error unless b200sht_plan_query(plan, 8) == 1. */
 int b200sht_fft_synthesis(const b200sht_plan* plan, const float* latspec, void* y, int dtype, int B, int C,
                           const float* bias, int scale_mode, void* stream);
 /* Legendre analysis  spec[l][m][..] = sum_k P[m][l][k] latspec[m][..][k]   (l >= 32*floor(m/32)) */
@@ -121,6 +121,11 @@ int b200sht_legendre_analysis(const b200sht_plan* plan, const float* latspec, fl
 /* Legendre synthesis latspec[m][..][k] = sum_l P[m][l][k] spec[l][m][..] */
 int b200sht_legendre_synthesis(const b200sht_plan* plan, const float* spec, float* latspec, int B, int C,
                                int precision, void* stream);
+/* Legendre synthesis (TF32) into the TILED latspec layout the tensor-core longitude DFT consumes:
+ *   latspec[r][k / 8][plane][m / 8][m % 8][k % 8]   (orders padded with zeros to a multiple of 8; same size as the standard layout)
+ * i.e. the 16 KB that one 8-row tile of the DFT kernel reads are contiguous and arrive as 128-byte TMA rows.  Pair it with
+ * b200sht_fft_synthesis(..., scale_mode | 2).  Requires b200sht_plan_query(plan, 8) == 1. */
+int b200sht_legendre_synthesis_tiled(const b200sht_plan* plan, const float* spec, float* latspec, int B, int C, void* stream);
 /* packed spec [L][M][2][B][cp] <-> torch complex64 [B*C][L][M] (exact zeros written for l < m).  These and the
  * mix / ComplexReLU entry points below depend only on the mode counts (L, M), not on a grid, so they take no plan. */
 int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream);

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "b200sht_fft_synthesis": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_int, _P]),
     "b200sht_legendre_analysis": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200sht_legendre_synthesis": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "b200sht_legendre_synthesis_tiled": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "b200sht_spec_unpack": (c_int, [c_int, c_int, _P, _P, c_int, c_int, _P]),
     "b200sht_spec_pack": (c_int, [c_int, c_int, _P, _P, c_int, c_int, _P]),
     "b200sht_spec_unpack_ex": (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P]),

@@ -43,7 +43,8 @@ int dft_plan_init(Plan* pl);
 void dft_plan_destroy(Plan* pl);
 int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out);
 int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st);
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st);
+bool dft_usable(const Plan* pl);
 int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
 int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
                       int Ci, int Co, cudaStream_t st);
@@ -152,7 +153,7 @@ int64_t b200sht_plan_query(const b200sht_plan* pl, int what) {
     case 5: return (int64_t)sizeof(float) * pl->mmax * pl->lmax * pl->kp;
     case 6: return pl->umma_ok;
     case 7: return pl->m0;
-    case 8: return pl->dft_state != nullptr;
+    case 8: return (pl->umma_ok && dft_usable(pl)) ? 1 : 0;
     default: return -1;
   }
 }
@@ -210,8 +211,28 @@ int b200sht_legendre_synthesis(const b200sht_plan* pl, const float* spec, float*
   B200_REQUIRE(!pl->no_table, "legendre_synthesis: FFT-only plan");
   int rc = check_precision(pl->umma_ok, precision, "legendre_synthesis");
   if (rc) return rc;
-  return precision == B200SHT_PREC_TF32 ? legendre_synthesis_umma(pl, spec, latspec, B, C, S(stream))
+  return precision == B200SHT_PREC_TF32 ? legendre_synthesis_umma(pl, spec, latspec, B, C, 0, S(stream))
                                         : legendre_synthesis_simt(pl, spec, latspec, B, C, S(stream));
+}
+
+int b200sht_legendre_synthesis_tiled(const b200sht_plan* pl, const float* spec, float* latspec, int B, int C, void* stream) {
+  B200_REQUIRE(pl && latspec && spec && B > 0 && C > 0, "legendre_synthesis_tiled: bad argument");
+  B200_REQUIRE(!pl->no_table, "legendre_synthesis_tiled: FFT-only plan");
+  B200_REQUIRE(pl->umma_ok && dft_usable(pl), "legendre_synthesis_tiled: the tensor-core DFT is not available for this plan (b200sht_plan_query(plan, 8) == 0)");
+  return legendre_synthesis_umma(pl, spec, latspec, B, C, 1, S(stream));
+}
+
+// Legendre synthesis + longitude synthesis: through the tiled latspec layout and the tensor-core DFT when the plan supports it at TF32
+static int synthesis_pair(const b200sht_plan* pl, const float* spec, float* lat, void* y, int dtype, int B, int C, const float* bias, int mode,
+                          int precision, void* stream) {
+  if (precision == B200SHT_PREC_TF32 && pl->umma_ok && dft_usable(pl)) {
+    int rc = b200sht_legendre_synthesis_tiled(pl, spec, lat, B, C, stream);
+    if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode | 2, stream);
+    return rc;
+  }
+  int rc = b200sht_legendre_synthesis(pl, spec, lat, B, C, precision, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode, stream);
+  return rc;
 }
 
 int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream) {
@@ -276,8 +297,7 @@ int b200sht_sht_inverse(const b200sht_plan* pl, const void* coeffs, void* y, int
   float *Z, *sp;
   split_ws(pl, B, C, ws, &Z, &sp);
   int rc = b200sht_spec_pack(pl->lmax, pl->mmax, coeffs, sp, B, C, stream);
-  if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(pl, Z, y, dtype, B, C, nullptr, 0 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
+  if (!rc) rc = synthesis_pair(pl, sp, Z, y, dtype, B, C, nullptr, 0, precision, stream);
   return rc;
 }
 
@@ -287,8 +307,7 @@ int b200sht_sht_forward_adjoint(const b200sht_plan* pl, const void* gcoeffs, voi
   float *Z, *sp;
   split_ws(pl, B, C, ws, &Z, &sp);
   int rc = b200sht_spec_pack(pl->lmax, pl->mmax, gcoeffs, sp, B, C, stream);
-  if (!rc) rc = b200sht_legendre_synthesis(pl, sp, Z, B, C, precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(pl, Z, gx, dtype, B, C, nullptr, 1 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
+  if (!rc) rc = synthesis_pair(pl, sp, Z, gx, dtype, B, C, nullptr, 1, precision, stream);
   return rc;
 }
 
@@ -413,17 +432,14 @@ int b200sht_spectral_conv_forward(const b200sht_plan* f, const b200sht_plan* v, 
   if (rc) return rc;
   B200_REQUIRE(x && w && y && workspace, "spectral_conv_forward: null argument");
   ConvWs ws = conv_ws(f, v, d, workspace);
-  const int tf = d->precision == B200SHT_PREC_TF32 ? 2 : 0;
   float* spec_x = spec_x_saved ? spec_x_saved : ws.spec_in;
   rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc) rc = b200sht_legendre_analysis(f, ws.lat_in, spec_x, d->B, d->Cin, d->precision, stream);
   if (!rc && residual) {
-    rc = b200sht_legendre_synthesis(v, spec_x, ws.lat_out, d->B, d->Cin, d->precision, stream);
-    if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0 | tf, stream);
+    rc = synthesis_pair(v, spec_x, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0, d->precision, stream);
   }
   if (!rc) rc = b200sht_mix_forward(f->lmax, f->mmax, d->op, spec_x, w, nullptr, ws.spec_out, d->B, d->G, d->Cin, d->Cout, d->precision, stream);
-  if (!rc) rc = b200sht_legendre_synthesis(v, ws.spec_out, ws.lat_out, d->B, d->Cout, d->precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(v, ws.lat_out, y, d->dtype, d->B, d->Cout, bias, 0 | tf, stream);
+  if (!rc) rc = synthesis_pair(v, ws.spec_out, ws.lat_out, y, d->dtype, d->B, d->Cout, bias, 0, d->precision, stream);
   return rc;
 }
 
@@ -456,8 +472,7 @@ int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v,
         B200_CHECK_LAUNCH();
       }
     }
-    if (!rc) rc = b200sht_legendre_synthesis(f, ws.spec_in, ws.lat_in, d->B, d->Cin, d->precision, stream);
-    if (!rc) rc = b200sht_fft_synthesis(f, ws.lat_in, gx, d->dtype, d->B, d->Cin, nullptr, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
+    if (!rc) rc = synthesis_pair(f, ws.spec_in, ws.lat_in, gx, d->dtype, d->B, d->Cin, nullptr, 1, d->precision, stream);
   }
   return rc;
 }

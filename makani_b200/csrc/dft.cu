@@ -37,6 +37,7 @@ struct DftTables {
   float* et;      // synthesis A: [2][128 rows = lane -> j2][32 m2]  (cos, sin), TF32-rounded
   float* eb;      // analysis  B: [nkb][2][32 rows m2][32 j2 local]  (cos, sin), TF32-rounded
   float2* tw;     // [8][N2]  exp(+2 pi i c j2 / nlon)
+  float* zeros;   // 8 * N2 floats of zeros: load target of the analysis lanes / rows that carry no sample (keeps the loads unconditional)
   int N2, half, M2, qpr, nrep, nkb;
 };
 
@@ -87,11 +88,13 @@ int dft_plan_init(Plan* pl) {
   t->qpr = (t->half + 1 + 31) / 32;
   t->nrep = t->qpr == 1 ? 4 : (t->qpr == 2 ? 2 : 1);
   t->nkb = t->qpr;
-  t->et = nullptr; t->eb = nullptr; t->tw = nullptr;
+  t->et = nullptr; t->eb = nullptr; t->tw = nullptr; t->zeros = nullptr;
   const size_t neb = (size_t)t->nkb * 2 * 32 * 32;
   cudaError_t e = cudaMalloc(&t->et, sizeof(float) * 2 * 128 * 32);
   if (e == cudaSuccess) e = cudaMalloc(&t->eb, sizeof(float) * neb);
   if (e == cudaSuccess) e = cudaMalloc(&t->tw, sizeof(float2) * 8 * t->N2);
+  if (e == cudaSuccess) e = cudaMalloc(&t->zeros, sizeof(float) * 8 * t->N2);
+  if (e == cudaSuccess) e = cudaMemset(t->zeros, 0, sizeof(float) * 8 * t->N2);
   if (e == cudaSuccess) {
     const int n = 8192 > 8 * t->N2 ? 8192 : 8 * t->N2;
     dft_tables_kernel<<<(n + 255) / 256, 256>>>(t->et, t->eb, t->tw, t->N2, t->half, t->M2, t->qpr, t->nrep, t->nkb, pl->nlon);
@@ -99,7 +102,7 @@ int dft_plan_init(Plan* pl) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   }
   if (e != cudaSuccess) {
-    cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw);
+    cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros);
     delete t;
     return -1;
   }
@@ -110,7 +113,7 @@ int dft_plan_init(Plan* pl) {
 void dft_plan_destroy(Plan* pl) {
   DftTables* t = static_cast<DftTables*>(pl->dft_state);
   if (!t) return;
-  cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw);
+  cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros);
   delete t;
   pl->dft_state = nullptr;
 }
@@ -184,19 +187,19 @@ template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfl
 
 // ================================================================================================ synthesis
 struct DftSynParams {
-  alignas(64) CUtensorMap tmZ;   // latspec as (k, c, m2, p, r), box (8, 4, 32, 1, 1): MN-major B operand, N = (c, k)
+  alignas(64) CUtensorMap tmZ;   // tiled latspec as ((c % 4, k % 8), c / 4, m2, p, tile), box (32, 1, 32, 1, 1): MN-major B operand, N = (c, k)
   alignas(64) CUtensorMap tmE;   // E^T tiles (m2, 256 rows), box (32, 128): K-major A operand
   const float* Z;
   void* y;
   const float2* tw;
   const float* rowscale;
   const float* bias;
-  int R, C, nlat, nlon, kp, mmax, N2, half, qpr, nrep, mode, ntiles, ktiles, has_nyq;
+  int R, C, nlat, nlon, kp, mmax, N2, half, M2, qpr, nrep, mode, ntiles, ktiles, has_nyq;
   uint32_t idesc;
 };
 
 // shared memory: [A: cos 16 KB | sin 16 KB][B ring: kDftSynStages x 16 KB][tw table 8 x N2 float2][barriers]
-template <typename T>
+template <typename T, int N2T>
 __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const __grid_constant__ DftSynParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   uint64_t* e_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int quad = warp & 3, sub = warp >> 2;
   const int subs = 4 / p.nrep;                                  // k pairs per replica
   const bool is_tma = (warp == 15), is_mma = (warp == 11);
@@ -241,15 +244,14 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
       tma_load_2d(sA + 16384, &p.tmE, e_full, 0, 128);
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-        const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 8;
         const int s = n % kDftSynStages, it = n / kDftSynStages;
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
         mbar_expect_tx(&full[s], 16384);
         const uint32_t st = sB + s * 16384;
-        tma_load_5d(st, &p.tmZ, &full[s], k0, 0, 0, 0, r);
-        tma_load_5d(st + 4096, &p.tmZ, &full[s], k0, 4, 0, 0, r);
-        tma_load_5d(st + 8192, &p.tmZ, &full[s], k0, 0, 0, 1, r);
-        tma_load_5d(st + 12288, &p.tmZ, &full[s], k0, 4, 0, 1, r);
+        tma_load_5d(st, &p.tmZ, &full[s], 0, 0, 0, 0, ti);           // re, classes 0..3
+        tma_load_5d(st + 4096, &p.tmZ, &full[s], 0, 1, 0, 0, ti);    // re, classes 4..7
+        tma_load_5d(st + 8192, &p.tmZ, &full[s], 0, 0, 0, 1, ti);    // im
+        tma_load_5d(st + 12288, &p.tmZ, &full[s], 0, 1, 0, 1, ti);
       }
     }
     __syncwarp();
@@ -281,31 +283,40 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
     }
     __syncwarp();
   } else if (is_epi) {
+    const int N2 = N2T > 0 ? N2T : p.N2;
+    const int nlon = 8 * N2;
     const int rep = quad / p.qpr;
     const int j2 = 32 * (quad - rep * p.qpr) + lane;
     const bool valid = j2 <= p.half;
-    const bool paired = valid && j2 != 0 && 2 * j2 != p.N2;
-    const int jp = p.N2 - j2;
+    const bool paired = valid && j2 != 0 && 2 * j2 != N2;
+    const int jp = N2 - j2;
     const int kpi = rep * subs + sub;
-    const int N2 = p.N2;
+    const bool n2odd = (N2 & 1) != 0;
     T* const y = static_cast<T*>(p.y);
     const float smul = p.mode == 0 ? 2.f : 1.f;
-    const int nyq_m = p.nlon / 2;
+    const int nyq_m = nlon / 2;
+    float2 tw[8], tp[8];
+    tw[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int c = 1; c < 8; ++c) tw[c] = valid ? tws[c * N2 + j2] : make_float2(1.f, 0.f);
+    dft_partner_twiddles(tw, tp);
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
       const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 8;
       const int ka = k0 + 2 * kpi;
       const int buf = n & 1, use = n >> 1;
-      // per-row output factors:  out = x * sc + off(parity)
+      // per-row output factors:  out = x * sc + off(parity of the longitude)
       float rsa = 1.f, rsb = 1.f, z0a = 0.f, z0b = 0.f, zna = 0.f, znb = 0.f;
       if (p.mode == 1) {
         const float2 rs = *reinterpret_cast<const float2*>(p.rowscale + ka);
         rsa = rs.x; rsb = rs.y;
       } else {
-        const float2 z0 = *reinterpret_cast<const float2*>(p.Z + (size_t)r * p.kp + ka);
+        // tiled latspec: element (m, plane, r, k) at ((tile * 2 + plane) * M2 + m / 8) * 64 + (m % 8) * 8 + k % 8, tile = r * ktiles + k / 8
+        const float* zt = p.Z + (size_t)ti * 2 * p.M2 * 64 + 2 * kpi;
+        const float2 z0 = *reinterpret_cast<const float2*>(zt);
         z0a = z0.x; z0b = z0.y;
         if (p.has_nyq) {
-          const float2 zn = *reinterpret_cast<const float2*>(p.Z + ((size_t)nyq_m * 2 * p.R + r) * p.kp + ka);
+          const float2 zn = *reinterpret_cast<const float2*>(zt + (nyq_m >> 3) * 64 + (nyq_m & 7) * 8);
           zna = zn.x; znb = zn.y;
         }
       }
@@ -330,37 +341,32 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
       if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the accumulators are in registers: release the set
       if (!valid) continue;
       const bool oka = ka < p.nlat, okb = ka + 1 < p.nlat;
-      T* const rowa = y + ((size_t)r * p.nlat + (oka ? ka : 0)) * p.nlon;
-      T* const rowb = rowa + p.nlon;
-      float2 tw[8];
-#pragma unroll
-      for (int c = 1; c < 8; ++c) tw[c] = tws[c * N2 + j2];
+      T* const pa = y + ((size_t)r * p.nlat + (oka ? ka : 0)) * nlon + j2;   // row a, column j2; row b = + nlon; partner = + (jp - j2)
       {
         pr vr[8], vi[8], x[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) { vr[c] = s1[c] - s2[c]; vi[c] = s3[c] + s4[c]; }
         dft_syn_radix8<pr>(vr, vi, tw, x);
+        const pr o0 = (j2 & 1) ? off_o : off_e, o1 = (j2 & 1) ? off_e : off_o;
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
-          const int j = N2 * j1 + j2;
-          const pr o = rfma(x[j1], sc, (j & 1) ? off_o : off_e);
-          if (oka) st_out<T>(rowa + j, o.v.x);
-          if (okb) st_out<T>(rowb + j, o.v.y);
+          const pr o = rfma(x[j1], sc, (n2odd && (j1 & 1)) ? o1 : o0);
+          if (oka) st_out<T>(pa + N2 * j1, o.v.x);
+          if (okb) st_out<T>(pa + nlon + N2 * j1, o.v.y);
         }
       }
       if (paired) {
-        float2 tp[8];
-        dft_partner_twiddles(tw, tp);
         pr vr[8], vi[8], x[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) { vr[c] = s1[c] + s2[c]; vi[c] = s4[c] - s3[c]; }
         dft_syn_radix8<pr>(vr, vi, tp, x);
+        T* const pq = pa + (jp - j2);
+        const pr o0 = (jp & 1) ? off_o : off_e, o1 = (jp & 1) ? off_e : off_o;
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
-          const int j = N2 * j1 + jp;
-          const pr o = rfma(x[j1], sc, (j & 1) ? off_o : off_e);
-          if (oka) st_out<T>(rowa + j, o.v.x);
-          if (okb) st_out<T>(rowb + j, o.v.y);
+          const pr o = rfma(x[j1], sc, (n2odd && (j1 & 1)) ? o1 : o0);
+          if (oka) st_out<T>(pq + N2 * j1, o.v.x);
+          if (okb) st_out<T>(pq + nlon + N2 * j1, o.v.y);
         }
       }
     }
@@ -382,15 +388,12 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   p.ktiles = pl->kp / 8; p.ntiles = R * p.ktiles;
   p.has_nyq = (pl->mmax == pl->nlon / 2 + 1) ? 1 : 0;
   p.idesc = make_idesc(64, 0, 1, 0);
-  // orders mmax .. 8 * M2 - 1 are read by the TMA boxes (class c, row m2 = M2 - 1): they must hold zeros.  The latspec buffers are
-  // sized for round_up(mmax, 8) planes (b200sht_latspec_elems); the pad planes are cleared here.
-  const size_t plane = (size_t)2 * R * pl->kp;
-  if (8 * t->M2 > pl->mmax)
-    B200_CHECK_CUDA(cudaMemsetAsync(const_cast<float*>(Z) + (size_t)pl->mmax * plane, 0, sizeof(float) * (size_t)(8 * t->M2 - pl->mmax) * plane, st));
+  p.M2 = t->M2;
   {
-    const long long rk = (long long)R * pl->kp;
-    long long d[5] = {pl->kp, 8, t->M2, 2, R}, s[5] = {1, 2 * rk, 16 * rk, rk, pl->kp};
-    int bx[5] = {8, 4, 32, 1, 1};
+    // tiled latspec (written by legendre_synthesis_umma(tiled = 1)): [tile = r * ktiles + k / 8][plane][m2][c = m % 8][k % 8]; a tile is 16 KB
+    // contiguous, the 128-byte rows of the TMA box are (4 classes x 8 latitudes) of one m2: the MN-major B operand, N = (c, k)
+    long long d[5] = {32, 2, t->M2, 2, (long long)R * (pl->kp / 8)}, s[5] = {1, 32, 64, (long long)t->M2 * 64, 2ll * t->M2 * 64};
+    int bx[5] = {32, 1, 32, 1, 1};
     int rc = make_tmap(&p.tmZ, Z, 5, d, s, bx, true);
     if (rc) return rc;
   }
@@ -403,13 +406,21 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   const size_t smem = 1024 + 32768 + (size_t)kDftSynStages * 16384 + ((8 * (size_t)t->N2 * 8 + 15) & ~(size_t)15) + (2 * kDftSynStages + 5) * 8 + 16;
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
-  if (dtype == B200SHT_BF16) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dft_synthesis_kernel<__nv_bfloat16><<<ctas, kDftSynThreads, smem, st>>>(p);
-  } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dft_synthesis_kernel<float><<<ctas, kDftSynThreads, smem, st>>>(p);
+#define B200_LAUNCH_SYN(TT, NN)                                                                                                          \
+  do {                                                                                                                                  \
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    dft_synthesis_kernel<TT, NN><<<ctas, kDftSynThreads, smem, st>>>(p);                                                                 \
+  } while (0)
+#define B200_DISPATCH_SYN(TT)                                            \
+  switch (t->N2) {                                                       \
+    case 180: B200_LAUNCH_SYN(TT, 180); break; /* nlon 1440 */           \
+    case 90: B200_LAUNCH_SYN(TT, 90); break;   /* nlon  720 */           \
+    case 60: B200_LAUNCH_SYN(TT, 60); break;   /* nlon  480 */           \
+    default: B200_LAUNCH_SYN(TT, 0); break;                              \
   }
+  if (dtype == B200SHT_BF16) { B200_DISPATCH_SYN(__nv_bfloat16) } else { B200_DISPATCH_SYN(float) }
+#undef B200_DISPATCH_SYN
+#undef B200_LAUNCH_SYN
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -421,13 +432,15 @@ struct DftAnaParams {
   float* X;
   const float2* tw;
   const float* rowscale;
+  const void* zeros;
   int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nslots;
   uint32_t idesc, idesc_neg;
 };
 
 // warps: 0..3 epilogue (TMEM quadrant = warp), 4 MMA issuer (+ TMEM owner, loads the resident B), 5.. producers
 // shared memory: [B resident: nkb x (cos 4 KB | sin 4 KB)][A ring: kDftAnaStages x 4 planes x 16 KB][barriers]
-template <typename T>
+// N2T > 0: nlon / 8 is a compile-time constant (sample offsets become immediates of the loads); 0: generic
+template <typename T, int N2T>
 __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
   uint64_t* b_full = acc_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int nkb = p.nkb;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDftAnaStages; ++s) { mbar_init(&full[s], p.nslots); mbar_init(&empty[s], 1); }
@@ -538,11 +551,12 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
     // after next are pulled into L2 by one prefetch per thread.  Lanes beyond N2/2 and rows beyond nlat carry zeros.
     const int pw = warp - 5;
     const int kb = pw % nkb, slot = pw / nkb;
+    const int N2 = N2T > 0 ? N2T : p.N2;
+    const int nlon = 8 * N2;
     const int j2 = 32 * kb + lane;
     const bool valid = j2 <= p.half;
-    const bool paired = valid && j2 != 0 && 2 * j2 != p.N2;
-    const int jp = p.N2 - j2;
-    const int N2 = p.N2;
+    const bool paired = valid && j2 != 0 && 2 * j2 != N2;
+    const int jp = paired ? N2 - j2 : j2;
     const int ipt = 16 / p.nslots;                 // items of this warp per tile (2 or 4)
     const int nprod = (int)(blockDim.x >> 5) - 5;  // producer warps
     float2 tw[8], tp[8];
@@ -559,25 +573,24 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
 #endif
     const T* const x = static_cast<const T*>(p.x);
     constexpr bool kBf16 = (sizeof(T) == 2);
-    auto load_item = [&](uint32_t* raw, int n, int i) {
-      const int ti = blockIdx.x + n * gridDim.x;
-      if (ti >= p.ntiles) return;
-      const int r = ti / p.ktiles, k = (ti - r * p.ktiles) * 16 + slot + i * p.nslots;
-      if (valid && k < p.nlat) {
-        const T* row = x + ((size_t)r * p.nlat + k) * p.nlon;
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ...  as (image r, row tile kt), advanced without divisions
+    const int dq = gridDim.x / p.ktiles, dr = gridDim.x - dq * p.ktiles;
+    auto advance = [&](int& r, int& kt) {
+      kt += dr; r += dq;
+      if (kt >= p.ktiles) { kt -= p.ktiles; ++r; }
+    };
+    const T* const zp = static_cast<const T*>(p.zeros);
+    auto load_item = [&](uint32_t* raw, int r, int kt, int i) {
+      // unconditional loads: lanes / rows without a sample read a page of zeros (no divergent region around the 16 loads)
+      const int k = kt * 16 + slot + i * p.nslots;
+      const bool ok = valid && r < p.R && k < p.nlat;
+      const T* row = x + ((size_t)(ok ? r : 0) * p.nlat + (ok ? k : 0)) * nlon;
+      const T* pa = ok ? row + j2 : zp;
+      const T* pb = (ok && paired) ? row + jp : zp;
 #pragma unroll
-        for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(row + N2 * j1 + j2);
-        if (paired) {
+      for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(pa + N2 * j1);
 #pragma unroll
-          for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(row + N2 * j1 + jp);
-        } else {
-#pragma unroll
-          for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = 0u;
-        }
-      } else {
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) raw[j1] = 0u;
-      }
+      for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(pb + N2 * j1);
     };
     auto compute_store = [&](const uint32_t* raw, float* stg, int kr) {
       float xa[8], xb[8], er[8], ei[8], br[8], bi[8];
@@ -603,16 +616,19 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       }
     };
     uint32_t rawA[16], rawB[16];
-    load_item(rawA, 0, 0);
-    int n = 0;
-    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+    int r = blockIdx.x / p.ktiles, kt = blockIdx.x - r * p.ktiles;
+    load_item(rawA, r, kt, 0);
+    for (int n = 0; r < p.R; ++n) {
+      int rn = r, ktn = kt;
+      advance(rn, ktn);
       {  // L2 prefetch of the tile after next (its samples are first touched ~2 tile times from now)
-        const int t2 = ti + 2 * gridDim.x;
-        if (t2 < p.ntiles) {
-          const int r2 = t2 / p.ktiles, k2 = (t2 - r2 * p.ktiles) * 16;
+        int r2 = rn, kt2 = ktn;
+        advance(r2, kt2);
+        if (r2 < p.R) {
+          const int k2 = kt2 * 16;
           const int rows = p.nlat - k2 < 16 ? p.nlat - k2 : 16;
-          const char* b2 = reinterpret_cast<const char*>(x + ((size_t)r2 * p.nlat + k2) * p.nlon);
-          const int lines = (int)(((size_t)rows * p.nlon * sizeof(T) + 127) >> 7);
+          const char* b2 = reinterpret_cast<const char*>(x + ((size_t)r2 * p.nlat + k2) * nlon);
+          const int lines = (int)(((size_t)rows * nlon * sizeof(T) + 127) >> 7);
           for (int l = pw * 32 + lane; l < lines; l += nprod * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)l * 128));
         }
       }
@@ -620,15 +636,16 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
       float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
       for (int i = 0; i < ipt; i += 2) {
-        load_item(rawB, n, i + 1);
+        load_item(rawB, r, kt, i + 1);
         compute_store(rawA, stg, slot + i * p.nslots);
-        if (i + 2 < ipt) load_item(rawA, n, i + 2);
-        else load_item(rawA, n + 1, 0);
+        if (i + 2 < ipt) load_item(rawA, r, kt, i + 2);
+        else load_item(rawA, rn, ktn, 0);
         compute_store(rawB, stg, slot + (i + 1) * p.nslots);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      r = rn; kt = ktn;
     }
   }
   tc_fence_before();
@@ -642,7 +659,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const int R = B * C;
   DftAnaParams p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale;
+  p.x = x; p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.zeros = t->zeros;
   p.R = R; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
   p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
@@ -660,13 +677,21 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
   const int threads = 32 * (5 + pwarps);
-  if (dtype == B200SHT_BF16) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dft_analysis_kernel<__nv_bfloat16><<<ctas, threads, smem, st>>>(p);
-  } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dft_analysis_kernel<float><<<ctas, threads, smem, st>>>(p);
+#define B200_LAUNCH_ANA(TT, NN)                                                                                                          \
+  do {                                                                                                                                  \
+    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    dft_analysis_kernel<TT, NN><<<ctas, threads, smem, st>>>(p);                                                                         \
+  } while (0)
+#define B200_DISPATCH_ANA(TT)                                            \
+  switch (t->N2) {                                                       \
+    case 180: B200_LAUNCH_ANA(TT, 180); break; /* nlon 1440 */           \
+    case 90: B200_LAUNCH_ANA(TT, 90); break;   /* nlon  720 */           \
+    case 60: B200_LAUNCH_ANA(TT, 60); break;   /* nlon  480 */           \
+    default: B200_LAUNCH_ANA(TT, 0); break;                              \
   }
+  if (dtype == B200SHT_BF16) { B200_DISPATCH_ANA(__nv_bfloat16) } else { B200_DISPATCH_ANA(float) }
+#undef B200_DISPATCH_ANA
+#undef B200_LAUNCH_ANA
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -863,8 +863,11 @@ int fft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
 int fft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int scale_mode, cudaStream_t st) {
   B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "fft_synthesis: B*C=%lld out of range", (long long)B * C);
   B200_REQUIRE(dtype == B200SHT_F32 || dtype == B200SHT_BF16, "fft_synthesis: unknown dtype %d", dtype);
-  if ((scale_mode & 2) && dft_usable(pl) && (reinterpret_cast<uintptr_t>(Z) & 15) == 0)
+  if (scale_mode & 2) {   // the input is in the tiled layout of b200sht_legendre_synthesis_tiled: only the tensor-core DFT reads it
+    B200_REQUIRE(dft_usable(pl), "fft_synthesis: scale_mode | 2 (tiled latspec, tensor-core DFT) is not available for this plan (b200sht_plan_query(plan, 8) == 0)");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(Z) & 127) == 0, "fft_synthesis: the tiled latspec must be 128-byte aligned");
     return dft_synthesis(pl, Z, y, dtype, B, C, bias, scale_mode & 1, st);
+  }
   FftParams prm = make_params(pl, B, C, scale_mode, bias);
   if (dtype == B200SHT_F32) return run_fft_dir<float>(pl, 1, Z, y, prm, st);
   if (dtype == B200SHT_BF16) return run_fft_dir<__nv_bfloat16>(pl, 1, Z, y, prm, st);

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   int* epi_scratch = reinterpret_cast<int*>(tmem_slot + 4);   // 2 x kEpiScratch ints, double-buffered by tile parity (epilogue warps only)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
@@ -196,6 +196,7 @@ struct SynTraits {
     alignas(64) CUtensorMap tmB;  // spec  (n, m, l)   box (32, 1, 32)   MN-major B (N = n)
     float* Z;
     int L, M, nlat, kp, C, cp, PB, nblk, N, m0;
+    int tiled, M2, KT, B;   // tiled output for the tensor-core DFT (dft.cu): Z[r][k / 8][p][m / 8][m % 8][k % 8], orders padded to 8 * M2
     uint32_t idesc;
   };
   struct Tile { int m, k0, n0, lbeg; };
@@ -207,7 +208,8 @@ struct SynTraits {
     return true;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
-  __device__ static int num_kblocks(const Params& p, const Tile& t) { return (p.L - t.lbeg + 31) / 32; }
+  // orders m >= M exist only in the tiled layout (padding up to a multiple of 8): no degree contributes, the tile is written as zeros
+  __device__ static int num_kblocks(const Params& p, const Tile& t) { return (t.m < p.M && t.lbeg < p.L) ? (p.L - t.lbeg + 31) / 32 : 0; }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
     const int l = t.lbeg + kb * 32;
 #pragma unroll
@@ -230,13 +232,21 @@ struct SynTraits {
       int o = -1;
       if (jp < JP) {
         const int pb = jp / p.cp, c = jp - pb * p.cp;
-        if (c < p.C) o = (pb * p.C + c) * p.kp;
+        if (c < p.C) {
+          if (!p.tiled) o = (pb * p.C + c) * p.kp;
+          else {   // pb = plane * B + b, image r = b * C + c:  Z[r][kt][plane][m2][c8][k8]
+            const int pl = pb / p.B, b = pb - pl * p.B;
+            o = (((b * p.C + c) * p.KT) * 2 + pl) * p.M2 * 64;
+          }
+        }
       }
       scratch[n] = o;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
     const bool kok = k < p.kp;
-    float* zb = p.Z + (size_t)t.m * p.PB * p.C * p.kp + (kok ? k : 0);
+    const int kk = kok ? k : 0;
+    float* zb = p.tiled ? p.Z + (size_t)(kk >> 3) * 2 * p.M2 * 64 + (t.m >> 3) * 64 + (t.m & 7) * 8 + (kk & 7)
+                        : p.Z + (size_t)t.m * p.PB * p.C * p.kp + kk;
     float v[32];
     for (int n0 = 0; n0 < p.N; n0 += 32) {
       if (t.n0 + n0 >= JP) break;
@@ -572,11 +582,13 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
   return launch<AnaTraits>(p, grid, st);
 }
 
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, cudaStream_t st) {
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st) {
   SynTraits::Params p;
   memset(&p, 0, sizeof(p));
   const int cp = round_up(C, 4), PB = 2 * B, JP = PB * cp;
   p.Z = Z; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.kp = pl->kp; p.C = C; p.cp = cp; p.PB = PB; p.m0 = pl->m0;
+  p.tiled = tiled; p.M2 = (pl->mmax + 7) / 8; p.KT = pl->kp / 8; p.B = B;
+  B200_REQUIRE(!tiled || (long long)B * C * p.KT * 2 * p.M2 * 64 < (1ll << 31), "legendre_synthesis: tiled latspec of %d images exceeds 2^31 floats", B * C);
   p.nblk = ceil_div(JP, 32) < 8 ? ceil_div(JP, 32) : 8;
   p.N = 32 * p.nblk;
   p.idesc = make_idesc(p.N, 1, 1, 0);
@@ -595,7 +607,7 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   pick_stages(&p, 16384 + 4096 * p.nblk, ceil_div(pl->lmax, 32));
   p.tx_bytes = 16384 + 4096 * p.nblk;
   set_accumulators(&p, p.N);
-  dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), pl->mmax);
+  dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), tiled ? 8 * p.M2 : pl->mmax);
   return launch<SynTraits>(p, grid, st);
 }
 

@@ -173,7 +173,7 @@ class _LocalFFT(torch.autograd.Function):
         lat = torch.empty(plan.latspec_elems(B, C), dtype=torch.float32, device=g.device)
         gx = torch.empty(ctx.shape, dtype=ctx.dtype, device=g.device)
         L.call("b200sht_latspec_pack", plan.handle, _p(g), _p(lat), B, C, _st(g.device))
-        L.call("b200sht_fft_synthesis", plan.handle, _p(lat), _p(gx), _dt(ctx.dtype), B, C, ctypes.c_void_p(0), 1 | (2 if ctx.prec == L.PREC_TF32 else 0), _st(g.device))
+        L.call("b200sht_fft_synthesis", plan.handle, _p(lat), _p(gx), _dt(ctx.dtype), B, C, ctypes.c_void_p(0), 1, _st(g.device))   # standard latspec layout (from the transposes): CUDA-core FFT
         return gx, None, None
 
 
@@ -185,7 +185,7 @@ class _LocalIFFT(torch.autograd.Function):
         lat = torch.empty(plan.latspec_elems(B, C), dtype=torch.float32, device=xc.device)
         y = torch.empty(B, C, plan.nlat, plan.nlon, dtype=dtype, device=xc.device)
         L.call("b200sht_latspec_pack", plan.handle, _p(xc), _p(lat), B, C, _st(xc.device))
-        L.call("b200sht_fft_synthesis", plan.handle, _p(lat), _p(y), _dt(dtype), B, C, ctypes.c_void_p(0), 0 | (2 if prec == L.PREC_TF32 else 0), _st(xc.device))
+        L.call("b200sht_fft_synthesis", plan.handle, _p(lat), _p(y), _dt(dtype), B, C, ctypes.c_void_p(0), 0, _st(xc.device))
         ctx.plan, ctx.prec = plan, prec
         return y
 

@@ -138,6 +138,16 @@ def get_plan(nlat, nlon, lmax, mmax, grid, csphase, device):
         return p
 
 
+def _synthesis_pair(plan, spec, lat, y, dtype, B, C, bias32, mode, precision, st):
+    """Legendre synthesis + longitude synthesis.  TF32 on a grid the tensor-core DFT covers: tiled latspec layout + dft.cu kernels."""
+    if precision == _lib.PREC_TF32 and plan.dft_ok:
+        _lib.call("b200sht_legendre_synthesis_tiled", plan.handle, _ptr(spec), _ptr(lat), B, C, st)
+        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), _dtype_code(dtype), B, C, _ptr(bias32), mode | 2, st)
+    else:
+        _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(spec), _ptr(lat), B, C, precision, st)
+        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), _dtype_code(dtype), B, C, _ptr(bias32), mode, st)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # autograd functions on packed tensors
 # ----------------------------------------------------------------------------------------------------------------
@@ -164,8 +174,7 @@ class _AnalysisPacked(torch.autograd.Function):
         lat = torch.empty(plan.latspec_elems(B, C), dtype=torch.float32, device=dev)
         gx = torch.empty(ctx.shape, dtype=ctx.dtype, device=dev)
         st = _stream(dev)
-        _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(gspec), _ptr(lat), B, C, ctx.precision, st)
-        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(gx), _dtype_code(ctx.dtype), B, C, _VP(0), 1 | (2 if ctx.precision == _lib.PREC_TF32 else 0), st)
+        _synthesis_pair(plan, gspec, lat, gx, ctx.dtype, B, C, None, 1, ctx.precision, st)
         return gx, None, None
 
 
@@ -182,8 +191,7 @@ class _SynthesisPacked(torch.autograd.Function):
         b32 = None
         if bias is not None:
             b32 = bias.detach().reshape(-1).to(torch.float32).contiguous()
-        _lib.call("b200sht_legendre_synthesis", plan.handle, _ptr(spec), _ptr(lat), B, C, precision, st)
-        _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), _dtype_code(dtype), B, C, _ptr(b32), 0 | (2 if precision == _lib.PREC_TF32 else 0), st)
+        _synthesis_pair(plan, spec, lat, y, dtype, B, C, b32, 0, precision, st)
         ctx.plan, ctx.precision, ctx.B, ctx.C = plan, precision, B, C
         ctx.has_bias = bias is not None
         ctx.bias_shape = tuple(bias.shape) if bias is not None else None

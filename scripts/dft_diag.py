@@ -23,9 +23,12 @@ ampc = amp[:nlat].cpu().double()
 bad = 0
 for m in list(range(min(mmax, 20))) + [mmax - 1]:
     for p in (0, 1):
-        lat = torch.zeros(plan.latspec_elems(B, C), device=dev)
-        Z = lat[: mmax * 2 * plan.kp].view(mmax, 2, plan.kp)
-        Z[m, p] = amp
+        Z = torch.zeros(mmax, 2, 1, plan.kp, device=dev)
+        Z[m, p, 0] = amp
+        M2 = (mmax + 7) // 8
+        Zp = torch.zeros(8 * M2, 2, 1, plan.kp, device=dev)
+        Zp[:mmax] = Z
+        lat = Zp.view(M2, 8, 2, 1, plan.kp // 8, 8).permute(3, 4, 2, 0, 1, 5).contiguous().reshape(-1)   # tiled layout
         y = torch.full((1, 1, nlat, nlon), float("nan"), device=dev)
         _lib.call("b200sht_fft_synthesis", plan.handle, _ptr(lat), _ptr(y), 0, B, C, _VP(0), 1 | 2, st)   # mode 1: y = rowscale * sum_m Re(Z e^{i m phi})
         torch.cuda.synchronize()

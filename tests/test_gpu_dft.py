@@ -34,6 +34,17 @@ def _latview(lat, plan, B, C, mmax):
     return lat[: mmax * 2 * B * C * plan.kp].view(mmax, 2, B * C, plan.kp)
 
 
+def to_tiled(Z, plan):
+    """standard latspec [mmax][2][R][kp] -> the tiled layout [R][kp/8][2][M2][8][8] (orders zero-padded to 8 * M2) that
+    b200sht_legendre_synthesis_tiled writes and b200sht_fft_synthesis(scale_mode | 2) reads (include/b200sht.h)"""
+    mmax, _, R, kp = Z.shape
+    M2 = (mmax + 7) // 8
+    Zp = torch.zeros(8 * M2, 2, R, kp, device=Z.device, dtype=Z.dtype)
+    Zp[:mmax] = Z
+    # (m2, c, p, r, kt, k8) -> (r, kt, p, m2, c, k8)
+    return Zp.view(M2, 8, 2, R, kp // 8, 8).permute(3, 4, 2, 0, 1, 5).contiguous().reshape(-1)
+
+
 @pytest.mark.parametrize("nlat,nlon,mmax,C,dtype", CASES)
 def test_dft_analysis_gpu(nlat, nlon, mmax, C, dtype):
     torch.manual_seed(333)
@@ -69,11 +80,11 @@ def test_dft_synthesis_gpu(nlat, nlon, mmax, C, dtype):
     assert plan.query(8) == 1
     B = 2
     st = mb.sht._stream(torch.device(DEV))
-    lat = torch.full((plan.latspec_elems(B, C),), float("nan"), device=DEV)     # the padding orders are cleared by the call
-    Z = _latview(lat, plan, B, C, mmax)
-    Z.copy_(torch.randn(mmax, 2, B * C, plan.kp, device=DEV))
+    Z = torch.randn(mmax, 2, B * C, plan.kp, device=DEV)
     # operands of the kind::tf32 GEMM are TF32 values in the product path (the Legendre epilogue rounds): do the same here
-    Z.copy_((Z.view(torch.int32) + 0x1000).bitwise_and(~0x1FFF).view(torch.float32))
+    Z = (Z.view(torch.int32) + 0x1000).bitwise_and(~0x1FFF).view(torch.float32)
+    lat = to_tiled(Z, plan)
+    assert lat.numel() == plan.latspec_elems(B, C)
     bias = torch.randn(C, device=DEV)
     Zc = torch.complex(Z[:, 0, :, :nlat], Z[:, 1, :, :nlat]).permute(1, 2, 0).reshape(B, C, nlat, mmax).to(torch.complex128).cpu()
     y = torch.full((B, C, nlat, nlon), float("nan"), device=DEV, dtype=dtype)
@@ -104,11 +115,28 @@ def test_dft_adjoint_pair_full_size():
     lat = torch.zeros(plan.latspec_elems(B, C), device=DEV)
     _lib.call("b200sht_fft_analysis", plan.handle, mb.sht._ptr(x), 0, B, C, mb.sht._ptr(lat), 0 | 2, st)
     Ax = _latview(lat, plan, B, C, mmax).clone()
-    lat2 = torch.zeros(plan.latspec_elems(B, C), device=DEV)
-    Z = _latview(lat2, plan, B, C, mmax)
-    Z.copy_(torch.randn_like(Z))
+    Z = torch.randn(mmax, 2, B * C, plan.kp, device=DEV)
+    lat2 = to_tiled(Z, plan)
     y = torch.empty(B, C, nlat, nlon, device=DEV)
     _lib.call("b200sht_fft_synthesis", plan.handle, mb.sht._ptr(lat2), mb.sht._ptr(y), 0, B, C, mb.sht._VP(0), 1 | 2, st)
     lhs = (Ax[..., :nlat].double() * Z[..., :nlat].double()).sum().item()
     rhs = (x.double() * y.double()).sum().item()
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
+@pytest.mark.parametrize("grid,nlat,nlon,lmax,mmax,B,C", [("equiangular", 64, 128, 64, 65, 1, 8), ("legendre-gauss", 48, 96, 32, 33, 2, 5), ("equiangular", 721, 1440, 240, 241, 1, 3)])
+def test_legendre_synthesis_tiled_is_a_relayout(grid, nlat, nlon, lmax, mmax, B, C):
+    """b200sht_legendre_synthesis_tiled writes exactly the values of b200sht_legendre_synthesis(TF32) in the tiled layout, with exact
+    zeros in the padding orders -- bit-identical (same kernel, different epilogue addressing)."""
+    torch.manual_seed(7)
+    plan = mb.get_plan(nlat, nlon, lmax, mmax, grid, True, torch.device(DEV))
+    assert plan.query(8) == 1
+    st = mb.sht._stream(torch.device(DEV))
+    sp = torch.randn(plan.spec_elems(B, C), device=DEV)
+    std = torch.full((plan.latspec_elems(B, C),), float("nan"), device=DEV)
+    til = torch.full((plan.latspec_elems(B, C),), float("nan"), device=DEV)
+    _lib.call("b200sht_legendre_synthesis", plan.handle, mb.sht._ptr(sp), mb.sht._ptr(std), B, C, _lib.PREC_TF32, st)
+    _lib.call("b200sht_legendre_synthesis_tiled", plan.handle, mb.sht._ptr(sp), mb.sht._ptr(til), B, C, st)
+    ref = to_tiled(_latview(std, plan, B, C, mmax), plan)
+    assert torch.isfinite(til).all()
+    assert torch.equal(til, ref)
