@@ -37,6 +37,7 @@ struct DftTables {
   float* et;      // synthesis A: [2][128 rows = lane -> j2][32 m2]  (cos, sin), TF32-rounded
   float* eb;      // analysis  B: [nkb][2][32 rows m2][32 j2 local]  (cos, sin), TF32-rounded
   float2* tw;     // [8][N2]  exp(+2 pi i c j2 / nlon)
+  float* trash;   // 64 x 4 * nlon floats: store target of the synthesis rows / lanes without output (keeps the stores unconditional); one slab per CTA % 64
   float* zeros;   // 8 * N2 floats of zeros: load target of the analysis lanes / rows that carry no sample (keeps the loads unconditional)
   int N2, half, M2, qpr, nrep, nkb;
 };
@@ -88,13 +89,14 @@ int dft_plan_init(Plan* pl) {
   t->qpr = (t->half + 1 + 31) / 32;
   t->nrep = t->qpr == 1 ? 4 : (t->qpr == 2 ? 2 : 1);
   t->nkb = t->qpr;
-  t->et = nullptr; t->eb = nullptr; t->tw = nullptr; t->zeros = nullptr;
+  t->et = nullptr; t->eb = nullptr; t->tw = nullptr; t->zeros = nullptr; t->trash = nullptr;
   const size_t neb = (size_t)t->nkb * 2 * 32 * 32;
   cudaError_t e = cudaMalloc(&t->et, sizeof(float) * 2 * 128 * 32);
   if (e == cudaSuccess) e = cudaMalloc(&t->eb, sizeof(float) * neb);
   if (e == cudaSuccess) e = cudaMalloc(&t->tw, sizeof(float2) * 8 * t->N2);
   if (e == cudaSuccess) e = cudaMalloc(&t->zeros, sizeof(float) * 8 * t->N2);
   if (e == cudaSuccess) e = cudaMemset(t->zeros, 0, sizeof(float) * 8 * t->N2);
+  if (e == cudaSuccess) e = cudaMalloc(&t->trash, sizeof(float) * 64 * 4 * pl->nlon);
   if (e == cudaSuccess) {
     const int n = 8192 > 8 * t->N2 ? 8192 : 8 * t->N2;
     dft_tables_kernel<<<(n + 255) / 256, 256>>>(t->et, t->eb, t->tw, t->N2, t->half, t->M2, t->qpr, t->nrep, t->nkb, pl->nlon);
@@ -102,7 +104,7 @@ int dft_plan_init(Plan* pl) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
   }
   if (e != cudaSuccess) {
-    cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros);
+    cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros); cudaFree(t->trash);
     delete t;
     return -1;
   }
@@ -113,7 +115,7 @@ int dft_plan_init(Plan* pl) {
 void dft_plan_destroy(Plan* pl) {
   DftTables* t = static_cast<DftTables*>(pl->dft_state);
   if (!t) return;
-  cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros);
+  cudaFree(t->et); cudaFree(t->eb); cudaFree(t->tw); cudaFree(t->zeros); cudaFree(t->trash);
   delete t;
   pl->dft_state = nullptr;
 }
@@ -194,6 +196,7 @@ struct DftSynParams {
   const float2* tw;
   const float* rowscale;
   const float* bias;
+  void* trash;
   int R, C, nlat, nlon, kp, mmax, N2, half, M2, qpr, nrep, mode, ntiles, ktiles, has_nyq;
   uint32_t idesc;
 };
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
     T* const y = static_cast<T*>(p.y);
     const float smul = p.mode == 0 ? 2.f : 1.f;
     const int nyq_m = nlon / 2;
+    T* const trash = static_cast<T*>(p.trash) + (size_t)(blockIdx.x & 63) * 4 * nlon;
     float2 tw[8], tp[8];
     tw[0] = make_float2(1.f, 0.f);
 #pragma unroll
@@ -327,46 +331,52 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
       mbar_wait(&acc_full[buf], use & 1);
       tc_fence_after();
       const uint32_t t0 = tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + 2 * kpi;
-      pr s1[8], s2[8], s3[8], s4[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        s1[c] = tmem_ld2(t0 + c * 8);
-        s2[c] = tmem_ld2(t0 + 64 + c * 8);
-        s3[c] = tmem_ld2(t0 + 128 + c * 8);
-        s4[c] = tmem_ld2(t0 + 192 + c * 8);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);   // the accumulators are in registers: release the set
-      if (!valid) continue;
-      const bool oka = ka < p.nlat, okb = ka + 1 < p.nlat;
-      T* const pa = y + ((size_t)r * p.nlat + (oka ? ka : 0)) * nlon + j2;   // row a, column j2; row b = + nlon; partner = + (jp - j2)
+      // rows beyond nlat (last tile of an image) are stored into a scratch row: no predicates / branches around the 32 stores
+      T* const pa = (valid && ka < p.nlat) ? y + ((size_t)r * p.nlat + ka) * nlon + j2 : trash + j2;
+      T* const pb = (valid && ka + 1 < p.nlat) ? y + ((size_t)r * p.nlat + ka + 1) * nlon + j2 : trash + nlon + j2;
+      const int dq = paired ? jp - j2 : 0;
+      // The four accumulators are read twice (TMEM reads are cheap) and reduced to V of one column right away, so that only 16 register
+      // pairs are live through each radix-8 pass: holding S1..S4 (64 registers) next to the twiddles made ptxas rematerialise the
+      // 64-bit store address for every one of the 32 stores (10 instructions each).
       {
         pr vr[8], vi[8], x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { vr[c] = s1[c] - s2[c]; vi[c] = s3[c] + s4[c]; }
+        for (int c = 0; c < 8; ++c) {
+          const pr a1 = tmem_ld2(t0 + c * 8), a2 = tmem_ld2(t0 + 64 + c * 8), a3 = tmem_ld2(t0 + 128 + c * 8), a4 = tmem_ld2(t0 + 192 + c * 8);
+          tmem_ld_wait();
+          vr[c] = a1 - a2;
+          vi[c] = a3 + a4;
+        }
         dft_syn_radix8<pr>(vr, vi, tw, x);
         const pr o0 = (j2 & 1) ? off_o : off_e, o1 = (j2 & 1) ? off_e : off_o;
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
           const pr o = rfma(x[j1], sc, (n2odd && (j1 & 1)) ? o1 : o0);
-          if (oka) st_out<T>(pa + N2 * j1, o.v.x);
-          if (okb) st_out<T>(pa + nlon + N2 * j1, o.v.y);
+          st_out<T>(pa + N2 * j1, o.v.x);
+          st_out<T>(pb + N2 * j1, o.v.y);
         }
       }
-      if (paired) {
+      {
         pr vr[8], vi[8], x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { vr[c] = s1[c] + s2[c]; vi[c] = s4[c] - s3[c]; }
+        for (int c = 0; c < 8; ++c) {
+          const pr a1 = tmem_ld2(t0 + c * 8), a2 = tmem_ld2(t0 + 64 + c * 8), a3 = tmem_ld2(t0 + 128 + c * 8), a4 = tmem_ld2(t0 + 192 + c * 8);
+          tmem_ld_wait();
+          vr[c] = a1 + a2;
+          vi[c] = a4 - a3;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);   // both reads done: release the accumulator set
         dft_syn_radix8<pr>(vr, vi, tp, x);
-        T* const pq = pa + (jp - j2);
+        T* const qa = paired ? pa + dq : trash + 2 * nlon + j2;     // unpaired columns (j2 = 0, N2 / 2) and idle lanes: scratch
+        T* const qb = paired ? pb + dq : trash + 3 * nlon + j2;
         const pr o0 = (jp & 1) ? off_o : off_e, o1 = (jp & 1) ? off_e : off_o;
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
           const pr o = rfma(x[j1], sc, (n2odd && (j1 & 1)) ? o1 : o0);
-          if (oka) st_out<T>(pq + N2 * j1, o.v.x);
-          if (okb) st_out<T>(pq + nlon + N2 * j1, o.v.y);
+          st_out<T>(qa + N2 * j1, o.v.x);
+          st_out<T>(qb + N2 * j1, o.v.y);
         }
       }
     }
@@ -382,7 +392,7 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   const int R = B * C;
   DftSynParams p;
   memset(&p, 0, sizeof(p));
-  p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias;
+  p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias; p.trash = t->trash;
   p.R = R; p.C = C; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.qpr = t->qpr; p.nrep = t->nrep; p.mode = mode;
   p.ktiles = pl->kp / 8; p.ntiles = R * p.ktiles;
@@ -483,12 +493,12 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
         const int buf = n & 3, use = n >> 2;
-        if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);
+        if (use > 0) mbar_wait_relaxed(&acc_empty[buf], (use - 1) & 1, 500);
         tc_fence_after();
         const uint32_t d = tmem + buf * 64;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
-          mbar_wait(&full[s], it & 1);
+          mbar_wait_relaxed(&full[s], it & 1, 300);   // the producers set the pace (~1.5 us per K-block): a late wake-up costs nothing
           tc_fence_after();
           const uint32_t st = sAr + s * 65536;
           const uint32_t bc = sBm + kb * 8192, bs = bc + 4096;
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       const int buf = n & 3, use = n >> 2;
       const bool kok = k < p.kp;
       const float rs = (p.mode == 0) ? ((k < p.nlat) ? __ldg(p.rowscale + k) : 0.f) : 1.f;
-      mbar_wait(&acc_full[buf], use & 1);
+      mbar_wait_relaxed(&acc_full[buf], use & 1, 1000);
       tc_fence_after();
       float vr[32], vi[32];
       const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16) + buf * 64;

@@ -58,6 +58,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// wait of a warp that is not on the critical path (epilogue / MMA issuer of a CUDA-core-bound kernel): poll every `ns` nanoseconds
+// instead of waking on every arrival, so that the waiting warps leave the issue slots to the working ones
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((++spins & 255u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000LL) {
+        printf("b200sht: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
