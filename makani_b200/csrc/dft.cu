@@ -181,6 +181,15 @@ __device__ __forceinline__ float tf32_operand_unscaled(float v) {   // class 0 c
 #endif
 }
 
+__device__ __forceinline__ pr pr_operand(pr v) { return make_pr(tf32_operand(v.v.x), tf32_operand(v.v.y)); }
+__device__ __forceinline__ pr pr_operand_unscaled(pr v) {
+#if B200_DFT_TF32_MODE == 2
+  return rmul(v, kTruncComp);
+#else
+  return pr_operand(v);
+#endif
+}
+
 template <typename T> __device__ __forceinline__ float ld_in(const T* p);
 template <> __device__ __forceinline__ float ld_in<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_in<__nv_bfloat16>(const __nv_bfloat16* p) {
@@ -466,11 +475,21 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
   uint64_t* acc_empty = acc_full + 4;
   uint64_t* b_full = acc_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float2* twS = reinterpret_cast<float2*>(gbase + 3 * 8192 + kDftAnaStages * 65536 + 256);   // [nkb][7][32] twiddles of the producer lanes
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int nkb = p.nkb;
+  for (int i = threadIdx.x; i < nkb * 7 * 32; i += blockDim.x) {
+    const int ln = i & 31, c = (i >> 5) % 7 + 1, kb = i / 224;
+    const int j2 = 32 * kb + ln;
+    float2 w = (j2 <= p.half) ? p.tw[c * p.N2 + j2] : make_float2(1.f, 0.f);
+#if B200_DFT_TF32_MODE == 2
+    w.x *= kTruncComp; w.y *= kTruncComp;
+#endif
+    twS[i] = w;
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kDftAnaStages; ++s) { mbar_init(&full[s], p.nslots); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kDftAnaStages; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }   // a K-block = 8 row pairs, one arrival each
     for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -560,28 +579,16 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
     // Latency: the samples of the NEXT item are in flight (registers) while the current one is computed, and the rows of the tile
     // after next are pulled into L2 by one prefetch per thread.  Lanes beyond N2/2 and rows beyond nlat carry zeros.
     const int pw = warp - 5;
-    const int kb = pw % nkb, slot = pw / nkb;
+    const int nprod = (int)(blockDim.x >> 5) - 5;  // producer warps: 12 (three K-blocks) or 8
     const int N2 = N2T > 0 ? N2T : p.N2;
     const int nlon = 8 * N2;
-    const int j2 = 32 * kb + lane;
-    const bool valid = j2 <= p.half;
-    const bool paired = valid && j2 != 0 && 2 * j2 != N2;
-    const int jp = paired ? N2 - j2 : j2;
-    const int ipt = 16 / p.nslots;                 // items of this warp per tile (2 or 4)
-    const int nprod = (int)(blockDim.x >> 5) - 5;  // producer warps
-    float2 tw[8], tp[8];
-#pragma unroll
-    for (int c = 1; c < 8; ++c) tw[c] = valid ? p.tw[c * N2 + j2] : make_float2(1.f, 0.f);
-    tw[0] = make_float2(1.f, 0.f);
-    dft_partner_twiddles(tw, tp);
-#if B200_DFT_TF32_MODE == 2
-#pragma unroll
-    for (int c = 1; c < 8; ++c) {
-      tw[c].x *= kTruncComp; tw[c].y *= kTruncComp;
-      tp[c].x *= kTruncComp; tp[c].y *= kTruncComp;
-    }
-#endif
+    // Work item = (K-block kb, row pair q): lanes are the 32 columns j2 of K-block kb, rows 2q and 2q + 1 of the tile travel in the two
+    // halves of packed f32x2 registers.  Items are taken in K-block-major order (item = kb * 8 + q; warp w does w, w + nprod, ...), so the
+    // first K-block of a tile is complete -- and its MMAs run -- while the warps are still producing the later ones, and the next tile's
+    // first K-block never waits for the tensor core (with one K-block per warp the producers idled ~15 % of the tile behind the MMAs).
+    const int items = 8 * nkb, ipw = items / nprod;
     const T* const x = static_cast<const T*>(p.x);
+    const T* const zp = static_cast<const T*>(p.zeros);
     constexpr bool kBf16 = (sizeof(T) == 2);
     // tiles of this CTA: blockIdx.x, + gridDim.x, ...  as (image r, row tile kt), advanced without divisions
     const int dq = gridDim.x / p.ktiles, dr = gridDim.x - dq * p.ktiles;
@@ -589,45 +596,30 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       kt += dr; r += dq;
       if (kt >= p.ktiles) { kt -= p.ktiles; ++r; }
     };
-    const T* const zp = static_cast<const T*>(p.zeros);
-    auto load_item = [&](uint32_t* raw, int r, int kt, int i) {
-      // unconditional loads: lanes / rows without a sample read a page of zeros (no divergent region around the 16 loads)
-      const int k = kt * 16 + slot + i * p.nslots;
-      const bool ok = valid && r < p.R && k < p.nlat;
-      const T* row = x + ((size_t)(ok ? r : 0) * p.nlat + (ok ? k : 0)) * nlon;
-      const T* pa = ok ? row + j2 : zp;
-      const T* pb = (ok && paired) ? row + jp : zp;
+    // eight samples of column j2 (or of its partner N2 - j2) of the two rows of an item: raw[0..7] row 0, raw[8..15] row 1.
+    // Unconditional loads: lanes / rows without a sample read a page of zeros.
+    auto load_col = [&](uint32_t* raw, int r, int kt, int item, bool partner) {
+      const int kb = item >> 3, k0 = kt * 16 + 2 * (item & 7);
+      const int j2 = 32 * kb + lane;
+      const bool valid = j2 <= p.half;
+      const bool use = partner ? (valid && j2 != 0 && 2 * j2 != N2) : valid;
+      const int jj = partner ? N2 - j2 : j2;
+      const bool ok0 = use && r < p.R && k0 < p.nlat, ok1 = use && r < p.R && k0 + 1 < p.nlat;
+      const T* p0 = ok0 ? x + ((size_t)r * p.nlat + k0) * nlon + jj : zp;
+      const T* p1 = ok1 ? p0 + nlon : zp;
 #pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(pa + N2 * j1);
+      for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(p0 + N2 * j1);
 #pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(pb + N2 * j1);
+      for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(p1 + N2 * j1);
     };
-    auto compute_store = [&](const uint32_t* raw, float* stg, int kr) {
-      float xa[8], xb[8], er[8], ei[8], br[8], bi[8];
+    auto unpack = [&](const uint32_t* raw, pr* xv) {
 #pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) {
-        xa[j1] = __uint_as_float(kBf16 ? raw[j1] << 16 : raw[j1]);
-        xb[j1] = __uint_as_float(kBf16 ? raw[8 + j1] << 16 : raw[8 + j1]);
-      }
-      dft_ana_radix8<float>(xa, tw, er, ei);
-      dft_ana_radix8<float>(xb, tp, br, bi);
-      // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8)
-      float* const dst = stg + kr * 32 + ((((lane >> 2) ^ (kr & 7)) << 2) | (lane & 3));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float ye_r = er[c] + br[c], yo_r = er[c] - br[c];
-        float ye_i = ei[c] + bi[c], yo_i = ei[c] - bi[c];
-        if (c == 0) { ye_r = tf32_operand_unscaled(ye_r); yo_r = tf32_operand_unscaled(yo_r); ye_i = 0.f; yo_i = 0.f; }
-        else { ye_r = tf32_operand(ye_r); yo_r = tf32_operand(yo_r); ye_i = tf32_operand(ye_i); yo_i = tf32_operand(yo_i); }
-        dst[c * 512] = ye_r;
-        dst[4096 + c * 512] = ye_i;
-        dst[8192 + c * 512] = yo_r;
-        dst[12288 + c * 512] = yo_i;
-      }
+      for (int j1 = 0; j1 < 8; ++j1)
+        xv[j1] = make_pr(__uint_as_float(kBf16 ? raw[j1] << 16 : raw[j1]), __uint_as_float(kBf16 ? raw[8 + j1] << 16 : raw[8 + j1]));
     };
     uint32_t rawA[16], rawB[16];
     int r = blockIdx.x / p.ktiles, kt = blockIdx.x - r * p.ktiles;
-    load_item(rawA, r, kt, 0);
+    load_col(rawA, r, kt, pw, false);
     for (int n = 0; r < p.R; ++n) {
       int rn = r, ktn = kt;
       advance(rn, ktn);
@@ -642,19 +634,50 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
           for (int l = pw * 32 + lane; l < lines; l += nprod * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)l * 128));
         }
       }
-      const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
-      if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
-      float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
-      for (int i = 0; i < ipt; i += 2) {
-        load_item(rawB, r, kt, i + 1);
-        compute_store(rawA, stg, slot + i * p.nslots);
-        if (i + 2 < ipt) load_item(rawA, r, kt, i + 2);
-        else load_item(rawA, rn, ktn, 0);
-        compute_store(rawB, stg, slot + (i + 1) * p.nslots);
+      for (int ii = 0; ii < ipw; ++ii) {
+        const int item = pw + ii * nprod;
+        const int kb = item >> 3, q = item & 7;
+        load_col(rawB, r, kt, item, true);              // partner column: in flight during the first butterfly
+        pr xv[8], er[8], ei[8], br[8], bi[8];
+        float2 tw[8], tp[8];
+        tw[0] = make_float2(1.f, 0.f);
+        const float2* const twl = twS + kb * 224 + lane;   // tw[c] = twl[(c - 1) * 32], already scaled for the truncation compensation
+#pragma unroll
+        for (int c = 1; c < 8; ++c) tw[c] = twl[(c - 1) * 32];
+        unpack(rawA, xv);
+        dft_ana_radix8<pr>(xv, tw, er, ei);
+        dft_partner_twiddles(tw, tp);   // products of the tw components with constants of modulus 1: they carry the (1 + f) factor too
+        unpack(rawB, xv);
+        dft_ana_radix8<pr>(xv, tp, br, bi);
+        if (ii + 1 < ipw) load_col(rawA, r, kt, item + nprod, false);   // next item's first column: in flight during the stores
+        else load_col(rawA, rn, ktn, pw, false);
+        const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
+        const int kr0 = 2 * q;
+        // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8);
+        // kr0 is even, so the second row is the next 128-byte line with the XOR term differing in bit 0
+        float* const d0 = stg + kr0 * 32 + ((((lane >> 2) ^ (kr0 & 7)) << 2) | (lane & 3));
+        float* const d1 = stg + (kr0 + 1) * 32 + ((((lane >> 2) ^ ((kr0 + 1) & 7)) << 2) | (lane & 3));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          pr ye_r = er[c] + br[c], yo_r = er[c] - br[c];
+          if (c == 0) { ye_r = pr_operand_unscaled(ye_r); yo_r = pr_operand_unscaled(yo_r); }
+          else { ye_r = pr_operand(ye_r); yo_r = pr_operand(yo_r); }
+          d0[c * 512] = ye_r.v.x; d1[c * 512] = ye_r.v.y;
+          d0[8192 + c * 512] = yo_r.v.x; d1[8192 + c * 512] = yo_r.v.y;
+          if (c == 0) {
+            d0[4096] = 0.f; d1[4096] = 0.f; d0[12288] = 0.f; d1[12288] = 0.f;
+          } else {
+            const pr ye_i = pr_operand(ei[c] + bi[c]), yo_i = pr_operand(ei[c] - bi[c]);
+            d0[4096 + c * 512] = ye_i.v.x; d1[4096 + c * 512] = ye_i.v.y;
+            d0[12288 + c * 512] = yo_i.v.x; d1[12288 + c * 512] = yo_i.v.y;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
       r = rn; kt = ktn;
     }
   }
@@ -683,7 +706,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
     int rc = make_tmap(&p.tmB, t->eb, 2, d, s, bx);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + (2 * kDftAnaStages + 9) * 8 + 16;
+  const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + 256 + (size_t)t->nkb * 7 * 32 * 8;
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
   const int threads = 32 * (5 + pwarps);
