@@ -237,6 +237,8 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload in MODEL_WORKLOADS:
+        return run_reference_model_arm(args)
     wl = args.workload
     cores, avail = pick_cpu_threads()
     steps = max(1, min(args.steps, 3))  # bounded: each step is a full fwd+bwd of the workload (~10 s of CPU work)
@@ -251,6 +253,31 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_reference_model_arm(args):
+    """CPU arm of the full-model workloads: the same network (makani_b200.sfno, pinned against the reference's network class by
+    tests/golden/sfno_golden.npz) on the oracle transforms / SpectralConv, bf16 autocast off (CPU), one bounded step."""
+    from makani_b200.sfno import SphericalFourierNeuralOperatorNet
+    from oracle.sfno_backend import OracleBackend
+
+    cfg = MODEL_WORKLOADS[args.workload]
+    cores, avail = pick_cpu_threads()
+    torch.manual_seed(333)
+    net = SphericalFourierNeuralOperatorNet(**cfg, backend=OracleBackend())
+    x = torch.randn(1, cfg["inp_chans"], *cfg["inp_shape"])
+    t0 = time.perf_counter()
+    out = net(x)
+    out.float().square().mean().backward()
+    t = time.perf_counter() - t0
+    val = 1.0 / t
+    print(json.dumps({
+        "impl": "reference", "metric": "SFNO model fwd+bwd samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_gpu": 1, "parallelism": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"1 full fwd+bwd step of the network on oracle/ (torch.fft + torch.einsum, fp32, {cores} threads of {avail})"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -579,13 +606,169 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- full-model workloads
+MODEL_WORKLOADS = {
+    # BASELINE configs[2]: config/sfnonet.yaml sfno_sc3_layers8_edim384 (inp_chans 77 = 73 + zenith + orography + 2 land masks, driver.py:180-257)
+    "sfno_sc3_layers8_edim384": dict(inp_shape=(721, 1440), out_shape=(721, 1440), inp_chans=77, out_chans=73, embed_dim=384, num_layers=8, scale_factor=3,
+                                     model_grid_type="equiangular", sht_grid_type="legendre-gauss", filter_type="linear", operator_type="dhconv", use_mlp=True,
+                                     mlp_ratio=2, activation_function="gelu", normalization_layer="instance_norm", hard_thresholding_fraction=1.0,
+                                     pos_embed="none", complex_activation="real", separable=False),
+    "sfno_tiny_model": dict(inp_shape=(49, 96), out_shape=(49, 96), inp_chans=7, out_chans=4, embed_dim=16, num_layers=3, scale_factor=3,
+                            model_grid_type="equiangular", sht_grid_type="legendre-gauss"),
+}
+
+
+def run_model_arm(args):
+    """fwd+bwd of the whole SFNO network (makani_b200.sfno on the CUDA kernels), bf16 autocast, loss = out.float().square().mean() (SURVEY cfg 3).
+    One rank per GPU, data parallel replicas when WORLD_SIZE > 1 (no gradient exchange timed here: the block bench covers that)."""
+    import makani_b200 as mb
+    from makani_b200 import _lib
+    from makani_b200.sfno import SphericalFourierNeuralOperatorNet
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = MODEL_WORKLOADS[args.workload]
+    precision = "tf32" if args.precision in ("best", "tf32") else "fp32"
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True     # makani/train.py:87
+    torch.manual_seed(333 + rank)
+    net = SphericalFourierNeuralOperatorNet(**cfg, precision=precision).to(dev)
+    act_dtype = torch.bfloat16 if args.act == "bf16" else torch.float32
+    x_host = torch.randn(1, cfg["inp_chans"], *cfg["inp_shape"]).pin_memory()
+    x_dev = x_host.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(xd):
+        for p_ in net.parameters():
+            p_.grad = None
+        with torch.autocast(device_type="cuda", dtype=act_dtype, enabled=(act_dtype == torch.bfloat16)):
+            out = net(xd)
+        loss = out.float().square().mean()
+        loss.backward()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        loss_host.copy_(step(xd).detach().reshape(1), non_blocking=True)
+
+    counter = {"n": 0}
+    per_call = {"b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
+                "b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1,
+                "b200sht_legendre_synthesis_tiled": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1, "b200sht_bias_grad": 1}
+    orig = _lib.call
+
+    def counting(name, *a):
+        counter["n"] += per_call.get(name, 0)
+        return orig(name, *a)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    try:
+        step(x_dev)
+        torch.cuda.synchronize()
+        _lib.call = counting
+        step(x_dev)
+        launches = counter["n"]
+        _lib.call = orig
+        if sampler:
+            sampler.start()
+            t_wait = time.perf_counter()
+            while not sampler.lines and time.perf_counter() - t_wait < 5.0:
+                step(x_dev)
+                torch.cuda.synchronize()
+        ms = timed(lambda: step(x_dev), args.steps, args.warmup)
+        clocks = sampler.stop() if sampler else None
+        ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    finally:
+        _lib.call = orig
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    lib = None
+    if not args.no_cpu and world == 1:
+        # the same network on this GPU through torch.fft + torch.einsum (cuFFT / cuBLAS): what torch-harmonics + makani dispatch to
+        try:
+            from oracle.sfno_backend import OracleBackend
+
+            del net
+            torch.cuda.empty_cache()
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+            ref = SphericalFourierNeuralOperatorNet(**cfg, backend=OracleBackend()).to(dev)
+
+            def ref_step():
+                for p_ in ref.parameters():
+                    p_.grad = None
+                with torch.autocast(device_type="cuda", dtype=act_dtype, enabled=(act_dtype == torch.bfloat16)):
+                    out = ref(x_dev)
+                out.float().square().mean().backward()
+
+            ms_lib = timed(ref_step, max(2, min(args.steps, 5)), 2)
+            lib = {"value": 1e3 / ms_lib, "unit": "samples/s", "ms_per_step": ms_lib,
+                   "what": "same network (makani_b200.sfno) with the spectral layers through torch.fft + torch.einsum on this GPU (cuFFT + cuBLAS, allow_tf32=True)"}
+        except Exception as e:  # noqa: BLE001
+            lib = {"error": str(e)[:300]}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    x_bytes = x_host.numel() * x_host.element_size()
+    line = {
+        "metric": "SFNO model fwd+bwd samples/sec", "value": world * 1e3 / ms, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast + " + precision, "data": "synthetic",
+        "config": {"workload": args.workload, "shape": [1, cfg["inp_chans"], *cfg["inp_shape"]], "activations": args.act, "batch_per_gpu": 1, "global_batch": world,
+                   "parallelism": f"dp{world} replicas" if world > 1 else "single", "embed_dim": cfg["embed_dim"], "num_layers": cfg["num_layers"],
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush)", "loss": "out.float().square().mean()"},
+        "clocks": clocks,
+        "e2e": {"value": world * 1e3 / ms_e2e, "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": x_bytes, "d2h_bytes_per_step": 4,
+                "how": "copy of the fp32 input from pinned host memory -> fwd+bwd -> read-back of the loss, one stream"},
+        "gpu_launches": launches,
+        "cpu_baseline": None,
+        "gpu_library_baseline": lib,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sfno_block_721x1440x73", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="sfno_block_721x1440x73", choices=sorted(WORKLOADS) + sorted(MODEL_WORKLOADS))
     ap.add_argument("--precision", default="best", choices=["best", "fp32", "tf32"])
     ap.add_argument("--act", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -597,7 +780,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
-        run_gpu_arm(args)
+        if args.workload in MODEL_WORKLOADS:
+            run_model_arm(args)
+        else:
+            run_gpu_arm(args)
 
 
 if __name__ == "__main__":

@@ -198,6 +198,15 @@ int b200sht_spectral_conv_backward(const b200sht_plan* fwd, const b200sht_plan* 
                                    const void* gy, const void* gresidual, const float* spec_x_saved, const void* w,
                                    void* gx, void* gw, float* gbias, void* workspace, void* stream);
 
+/* same, plus (both optional): gw_native receives the weight gradient re-laid-out to the parameter's native complex64 layout (dense operators)
+ * and wgrad_ready_event (a cudaEvent_t) is recorded on `stream` as soon as the weight / bias gradients are final, i.e. BEFORE the two stages
+ * that produce gx -- a data-parallel gradient all-reduce waiting on it from another stream overlaps them.  (The reference reaches the same
+ * overlap through DDP gradient hooks, makani/mpu/mappings.py:398-406 init_gradient_reduction_hooks.) */
+int b200sht_spectral_conv_backward_ex(const b200sht_plan* fwd, const b200sht_plan* inv, const b200sht_conv_desc* d,
+                                      const void* gy, const void* gresidual, const float* spec_x_saved, const void* w,
+                                      void* gx, void* gw, float* gbias, void* workspace, void* gw_native, void* wgrad_ready_event,
+                                      void* stream);
+
 /* sum over batch and latitude of latspec[m=0][re][b][c][k]: d(loss)/d(bias) when latspec = fft_analysis(gy, mode 1) */
 int b200sht_bias_grad(const b200sht_plan* plan, const float* latspec, float* gbias, int B, int C, void* stream);
 

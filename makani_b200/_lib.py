@@ -65,6 +65,7 @@ _SIGNATURES = {
     "b200sht_spectral_conv_workspace_bytes": (c_int64, [_P, _P, _P]),
     "b200sht_spectral_conv_forward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200sht_spectral_conv_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200sht_spectral_conv_backward_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200sht_bias_grad": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "b200sht_spectral_conv_forward_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     # debug / CPU-testable entry points (same device code compiled for the host)

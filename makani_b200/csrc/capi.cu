@@ -451,6 +451,12 @@ __global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, 
 
 int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, const void* gy, const void* gresidual,
                                    const float* spec_x_saved, const void* w, void* gx, void* gw, float* gbias, void* workspace, void* stream) {
+  return b200sht_spectral_conv_backward_ex(f, v, d, gy, gresidual, spec_x_saved, w, gx, gw, gbias, workspace, nullptr, nullptr, stream);
+}
+
+int b200sht_spectral_conv_backward_ex(const b200sht_plan* f, const b200sht_plan* v, const b200sht_conv_desc* d, const void* gy, const void* gresidual,
+                                      const float* spec_x_saved, const void* w, void* gx, void* gw, float* gbias, void* workspace,
+                                      void* gw_native, void* wgrad_ready_event, void* stream) {
   int rc = check_conv(f, v, d);
   if (rc) return rc;
   B200_REQUIRE(gy && w && workspace, "spectral_conv_backward: null argument");
@@ -462,6 +468,14 @@ int b200sht_spectral_conv_backward(const b200sht_plan* f, const b200sht_plan* v,
   if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cout, d->precision, stream);
   if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, gx ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G, d->Cin, d->Cout,
                                      d->precision, stream);
+  // the weight gradient is final here: hand it to the caller (native layout + event) BEFORE the two input-gradient stages, so that a
+  // data-parallel all-reduce on another stream overlaps legendre_synthesis + fft_synthesis instead of trailing the whole backward pass
+  if (!rc && gw && gw_native) {
+    const bool dense = (d->op == B200SHT_OP_DHCONV || d->op == B200SHT_OP_SHARED || d->op == B200SHT_OP_LDEP);
+    B200_REQUIRE(dense, "spectral_conv_backward_ex: gw_native is for the packed (dense) operators; the others already return the native layout");
+    rc = b200sht_mix_weight_unpack(d->op, static_cast<const float*>(gw), gw_native, f->lmax, d->G, d->Cin, d->Cout, stream);
+  }
+  if (!rc && wgrad_ready_event) B200_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(wgrad_ready_event), S(stream)));
   if (!rc && gx) {
     if (gresidual) {
       rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);

@@ -138,6 +138,7 @@ class _SpectralConvOneCall(torch.autograd.Function):
         ctx.save_for_backward(spec_saved, wdev)
         ctx.meta = (pf, pi, (B, mod.in_channels, mod.out_channels, mod.num_groups, op, _dtype_code(x.dtype), prec), tuple(x.shape), x.dtype,
                     tuple(weight.shape), None if bias is None else (tuple(bias.shape), bias.dtype), L, M, wsb)
+        ctx.wgrad_event = getattr(mod, "wgrad_ready_event", None)
         return (y, res) if res is not None else y
 
     @staticmethod
@@ -161,15 +162,13 @@ class _SpectralConvOneCall(torch.autograd.Function):
             else:
                 gw_dev = torch.empty(wshape, dtype=torch.complex64, device=dev)
         gb = torch.empty(Co, dtype=torch.float32, device=dev) if need_b else None
-        _lib.call("b200sht_spectral_conv_backward", pf.handle, pi.handle, dptr, _ptr(gy), _ptr(gres), _ptr(spec_saved), _ptr(wdev), _ptr(gx), _ptr(gw_dev),
-                  _ptr(gb), _ptr(ws), _stream(dev))
+        # the weight gradient is re-laid-out and its event recorded inside the call, before the input-gradient stages (b200sht.h)
         gw = None
         if need_w:
-            if op in _DENSE_OPS:
-                gw = torch.empty(wshape, dtype=torch.complex64, device=dev)
-                _lib.call("b200sht_mix_weight_unpack", op, _ptr(gw_dev), _ptr(gw), L, G, Ci, Co, _stream(dev))
-            else:
-                gw = gw_dev
+            gw = torch.empty(wshape, dtype=torch.complex64, device=dev) if op in _DENSE_OPS else gw_dev
+        ev = ctx.wgrad_event
+        _lib.call("b200sht_spectral_conv_backward_ex", pf.handle, pi.handle, dptr, _ptr(gy), _ptr(gres), _ptr(spec_saved), _ptr(wdev), _ptr(gx), _ptr(gw_dev),
+                  _ptr(gb), _ptr(ws), _ptr(gw) if (need_w and op in _DENSE_OPS) else _VP(0), _VP(ev.cuda_event) if ev is not None else _VP(0), _stream(dev))
         gbias = gb.reshape(binfo[0]).to(binfo[1]) if need_b else None
         return gx, gw, gbias, None
 
