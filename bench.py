@@ -280,6 +280,67 @@ def run_reference_model_arm(args):
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
+HXW_GRID = {2: (1, 2), 4: (2, 2), 8: (4, 2)}   # h x w spatial model-parallel grids (cfg 4 of BASELINE.json is h = 4, w = 2)
+
+
+def hxw_measure(wl, world, rank, dev, act_dtype, precision, steps, warmup):
+    """The SAME block with ONE sample split over all ranks (h x w spatial model parallelism, makani_b200.distributed: latitude over h, longitude
+    over w, l over h, m over w; 4 all-to-all transposes per distributed transform, makani/mpu/mappings.py:38-67).  Strong scaling: global batch 1.
+    Returns a dict for the JSON line (never raises: an h x w failure must not lose the data-parallel line)."""
+    import torch.distributed as dist
+
+    try:
+        import makani_b200 as mb
+        import makani_b200.distributed as mbd
+
+        h, w = HXW_GRID[world]
+        nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, L, M, C = WORKLOADS[wl]
+        h_groups = [dist.new_group([ih * w + iw for ih in range(h)]) for iw in range(w)]
+        w_groups = [dist.new_group([ih * w + iw for iw in range(w)]) for ih in range(h)]
+        ih, iw = rank // w, rank % w
+        mbd.init(h_groups[iw] if h > 1 else None, w_groups[ih] if w > 1 else None)
+        fd = mbd.DistributedRealSHT(nlat_i, nlon_i, L, M, grid_i, precision=precision)
+        idd = mbd.DistributedInverseRealSHT(nlat_o, nlon_o, L, M, grid_o, precision=precision)
+        torch.manual_seed(333)
+        conv = mb.SpectralConv(fd, idd, C, C, operator_type="dhconv", precision=precision).to(dev)
+        conv._wcache.enabled = False
+        x = torch.randn(1, C, fd.lat_shapes[ih], fd.lon_shapes[iw], device=dev).to(act_dtype)
+        gy = torch.randn(1, C, idd.lat_shapes[ih], idd.lon_shapes[iw], device=dev).to(act_dtype)
+        wg = w_groups[ih] if w > 1 else None
+
+        def step():
+            x.requires_grad_(True)
+            conv.weight.grad = None
+            y, _ = conv(x)
+            y.backward(gy)
+            x.grad = None
+            x.requires_grad_(False)
+            if wg is not None:   # the dhconv weight shard is shared over w (spectral_convolution.py:195-198)
+                dist.all_reduce(torch.view_as_real(conv.weight.grad), group=wg)
+
+        for _ in range(max(3, warmup)):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        mbd.finalize() if hasattr(mbd, "finalize") else None
+        return {"h": h, "w": w, "ms_per_step": ms, "value": 1e3 / ms, "unit": "samples/s", "scaling": "strong", "global_batch": 1,
+                "local_input": [1, C, fd.lat_shapes[ih], fd.lon_shapes[iw]], "lat_shapes": list(fd.lat_shapes), "m_shapes": list(fd.m_shapes),
+                "what": "one sample of the same block split over all ranks (latitude over h, longitude over w); NCCL all-to-all transposes + "
+                        "weight-gradient all-reduce over w inside the timed step; max over ranks"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
     import torch.distributed as dist
@@ -420,10 +481,20 @@ def run_gpu_arm(args):
             ms = t.item()
         return ms
 
+    # data parallel: the weight-gradient all-reduce is launched on a side stream as soon as the gradient is final (event recorded inside
+    # b200sht_spectral_conv_backward_ex, before the two input-gradient stages), so it overlaps legendre_synthesis + fft_synthesis
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    if world > 1:
+        conv.wgrad_ready_event = torch.cuda.Event()
+
     def dp_step():
         step(x_dev)
         if world > 1:
-            dist.all_reduce(torch.view_as_real(conv.weight.grad))
+            side.wait_event(conv.wgrad_ready_event)
+            with torch.cuda.stream(side):
+                dist.all_reduce(torch.view_as_real(conv.weight.grad))
+            conv.weight.grad.record_stream(side)
+            torch.cuda.current_stream(dev).wait_stream(side)
 
     # kernel launches of OUR library inside one step (counted by the ctypes call wrapper)
     counter = {"n": 0}
@@ -472,6 +543,10 @@ def run_gpu_arm(args):
         ms_e2e = e2e_pipelined(args.steps)
     finally:
         _lib.call = orig_call
+
+    hxw = None
+    if world in HXW_GRID and not args.no_hxw:
+        hxw = hxw_measure(wl, world, rank, dev, act_dtype, precision, max(3, min(args.steps, 10)), args.warmup)
 
     # ---- per-stage kernel timings (CUDA events, L2 flushed before each launch) -> roofline
     stages = {}
@@ -601,6 +676,8 @@ def run_gpu_arm(args):
     }
     if graph_info is not None:
         line["cuda_graph_replay"] = graph_info
+    if hxw is not None:
+        line["hxw"] = hxw
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -773,6 +850,7 @@ def main():
     ap.add_argument("--act", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stages", action="store_true", help="skip per-stage kernel timing")
+    ap.add_argument("--no-hxw", action="store_true", help="N > 1: skip the additional h x w spatial-model-parallel measurement of the same block")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph (opt-in experiment, N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":

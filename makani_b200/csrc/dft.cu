@@ -512,12 +512,12 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
         const int buf = n & 3, use = n >> 2;
-        if (use > 0) mbar_wait_relaxed(&acc_empty[buf], (use - 1) & 1, 500);
+        if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);
         tc_fence_after();
         const uint32_t d = tmem + buf * 64;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
-          mbar_wait_relaxed(&full[s], it & 1, 300);   // the producers set the pace (~1.5 us per K-block): a late wake-up costs nothing
+          mbar_wait(&full[s], it & 1);   // precise wake-up: the stage is released (empty) only after these MMAs, and the ring is one tile deep
           tc_fence_after();
           const uint32_t st = sAr + s * 65536;
           const uint32_t bc = sBm + kb * 8192, bs = bc + 4096;
@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       const int buf = n & 3, use = n >> 2;
       const bool kok = k < p.kp;
       const float rs = (p.mode == 0) ? ((k < p.nlat) ? __ldg(p.rowscale + k) : 0.f) : 1.f;
+      const float tcomp = p.round_tf32 ? kTruncComp : 1.f;
       mbar_wait_relaxed(&acc_full[buf], use & 1, 1000);
       tc_fence_after();
       float vr[32], vi[32];
@@ -562,9 +563,10 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
       for (int m2 = 0; m2 < 32; ++m2) {
         const int m = c + 8 * m2;
         if (m >= p.mmax) break;
-        const float sc = (p.mode == 0) ? rs : ((m == 0 || 2 * m == p.nlon) ? 1.f : 2.f);
-        float a = vr[m2] * sc, b = vi[m2] * sc;
-        if (p.round_tf32) { a = tf32_rn(a); b = tf32_rn(b); }
+        // round_tf32: the consumer is the kind::tf32 Legendre GEMM, which truncates its operands -> bias-compensated truncation folded
+        // into the scale factor (see B200_DFT_TF32_MODE above) instead of 3 instructions of cvt.rna per value
+        const float sc = ((p.mode == 0) ? rs : ((m == 0 || 2 * m == p.nlon) ? 1.f : 2.f)) * tcomp;
+        const float a = vr[m2] * sc, b = vi[m2] * sc;
         float* dst = xb + (size_t)m * 2 * plane;
         dst[0] = a;
         dst[plane] = b;
