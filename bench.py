@@ -502,7 +502,9 @@ def run_gpu_arm(args):
                         "b200sht_mix_forward": 1, "b200sht_mix_backward": 2, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
                         "b200sht_bias_grad": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1,
                         # one-call entry points: fft + legendre + mix + legendre + fft / fft + legendre + dgrad + wgrad + legendre + fft
-                        "b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6}
+                        "b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6,
+                        "b200sht_spectral_conv_backward_ex": 7,   # + the weight-gradient re-layout, now inside the call
+                        "b200sht_legendre_synthesis_tiled": 1}
     orig_call = _lib.call
 
     def counting_call(name, *a):
@@ -761,7 +763,7 @@ def run_model_arm(args):
         loss_host.copy_(step(xd).detach().reshape(1), non_blocking=True)
 
     counter = {"n": 0}
-    per_call = {"b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
+    per_call = {"b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6, "b200sht_spectral_conv_backward_ex": 7, "b200sht_mix_weight_pack": 1, "b200sht_mix_weight_unpack": 1,
                 "b200sht_fft_analysis": 1, "b200sht_fft_synthesis": 1, "b200sht_legendre_analysis": 1, "b200sht_legendre_synthesis": 1,
                 "b200sht_legendre_synthesis_tiled": 1, "b200sht_spec_pack": 1, "b200sht_spec_unpack": 1, "b200sht_bias_grad": 1}
     orig = _lib.call

@@ -192,6 +192,10 @@ inline PFN_encodeTiled get_encode() {
 inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides, const int* box, bool mn_major = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context.  A thread that has made no runtime call yet (PyTorch's autograd
+  // thread entering a backward whose first action is this encode) has none -> CUDA_ERROR_INVALID_CONTEXT (201).  Bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }

@@ -33,6 +33,11 @@ class OracleSpectralConv(nn.Module):
 
     def forward(self, x):
         bias = self.bias if hasattr(self, "bias") else None
+        with torch.autocast(device_type=x.device.type, enabled=False):     # transforms in fp32, as spectral_convolution.py:237-253
+            y, res = self._fwd(x.float(), bias)
+        return y.to(x.dtype), res.to(x.dtype)
+
+    def _fwd(self, x, bias):
         return O.spectral_conv_forward(x, self.weight, self.forward_transform, self.inverse_transform, num_groups=self.num_groups,
                                        operator_type=self.operator_type, separable=self.separable, bias=bias)
 
