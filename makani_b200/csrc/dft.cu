@@ -31,7 +31,6 @@ int umma_available();   // umma.cu
 constexpr int kDftMaxHalf = 95;    // N2 / 2 <= 95: three 32-lane quadrants (synthesis) / three K-blocks (analysis)
 constexpr int kDftSynThreads = 512;
 constexpr int kDftSynStages = 8;   // 16 KB each
-constexpr int kDftAnaStages = 3;   // 64 KB each
 
 struct DftTables {
   float* et;      // synthesis A: [2][128 rows = lane -> j2][32 m2]  (cos, sin), TF32-rounded
@@ -445,44 +444,55 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
 }
 
 // ================================================================================================= analysis
+constexpr int kDftAnaStages = 2;   // operand ring: one stage = one K-block (32 columns) of a 16-row tile = 4 planes x 16 KB
+
 struct DftAnaParams {
   alignas(64) CUtensorMap tmB;   // E tiles (32 j2 local, nkb * 64 rows), box (32, 32): K-major B operand
-  const void* x;
+  alignas(64) CUtensorMap tmX;   // the input as a matrix [R * nlat rows][nlon], box (32 columns, 16 rows), no swizzle
   float* X;
   const float2* tw;
   const float* rowscale;
-  const void* zeros;
-  int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nslots;
+  int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nraw;
   uint32_t idesc, idesc_neg;
 };
 
-// warps: 0..3 epilogue (TMEM quadrant = warp), 4 MMA issuer (+ TMEM owner, loads the resident B), 5.. producers
-// shared memory: [B resident: nkb x (cos 4 KB | sin 4 KB)][A ring: kDftAnaStages x 4 planes x 16 KB][barriers]
-// N2T > 0: nlon / 8 is a compile-time constant (sample offsets become immediates of the loads); 0: generic
+// warps: 0..3 epilogue (TMEM quadrant = warp), 4 MMA issuer (+ TMEM owner, loads the resident B), 5 sample loader (TMA), 6.. producers
+// shared memory: [B resident: nkb x (cos 4 KB | sin 4 KB)][A ring: 2 x 4 planes x 16 KB][raw ring: nraw x 16 boxes][twiddles][barriers]
+//
+// Data flow of one (tile, K-block): the loader thread brings the 8 + 8 sample boxes the K-block needs -- for each j1 the 32 columns
+// j2 = 32 kb .. + 31 and their 32 partner columns N2 - j2, 16 rows each -- into a raw stage with 16 TMA boxes (deep asynchronous prefetch,
+// no registers: the first version's LDG -> register path stalled 2.1 cycles per issued instruction on the loads, with the 96-register cap
+// allowing only half an item of prefetch).  Eight producer warps (one row pair each) read their samples with LDS, run the two radix-8
+// butterflies + twiddles with the two rows packed in f32x2, and write Ye / Yo of the 8 classes into the operand stage; then the MMA thread
+// contracts the stage with E.  N2T > 0: nlon / 8 as a compile-time constant.
 template <typename T, int N2T>
-__global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
+__global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t sBm = base;                            // resident E
-  const uint32_t sAr = base + 3 * 8192;                 // A ring (1024-aligned: 24576)
-  uint8_t* gA = gbase + 3 * 8192;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + 3 * 8192 + kDftAnaStages * 65536);
-  uint64_t* full = bars;
+  constexpr uint32_t kRawBytes = 16u * 16u * 32u * sizeof(T);   // 16 boxes x 16 rows x 32 columns
+  const uint32_t oB = 0, oA = 3 * 8192, oR = oA + kDftAnaStages * 65536, oT = oR + (uint32_t)p.nraw * kRawBytes, oBar = oT + 3 * 7 * 32 * 8;
+  const uint32_t sBm = base + oB, sAr = base + oA, sRaw = base + oR;
+  uint8_t* gA = gbase + oA;
+  const uint8_t* gR = gbase + oR;
+  float2* twS = reinterpret_cast<float2*>(gbase + oT);   // [nkb][7][32] twiddles of the producer lanes
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + oBar);
   uint64_t* empty = full + kDftAnaStages;
   uint64_t* acc_full = empty + kDftAnaStages;
   uint64_t* acc_empty = acc_full + 4;
-  uint64_t* b_full = acc_empty + 4;
+  uint64_t* raw_full = acc_empty + 4;
+  uint64_t* raw_empty = raw_full + 4;
+  uint64_t* b_full = raw_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-  float2* twS = reinterpret_cast<float2*>(gbase + 3 * 8192 + kDftAnaStages * 65536 + 256);   // [nkb][7][32] twiddles of the producer lanes
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int nkb = p.nkb;
+  const int N2 = N2T > 0 ? N2T : p.N2;
   for (int i = threadIdx.x; i < nkb * 7 * 32; i += blockDim.x) {
     const int ln = i & 31, c = (i >> 5) % 7 + 1, kb = i / 224;
     const int j2 = 32 * kb + ln;
-    float2 w = (j2 <= p.half) ? p.tw[c * p.N2 + j2] : make_float2(1.f, 0.f);
+    float2 w = (j2 <= p.half) ? p.tw[c * N2 + j2] : make_float2(1.f, 0.f);
 #if B200_DFT_TF32_MODE == 2
     w.x *= kTruncComp; w.y *= kTruncComp;
 #endif
@@ -491,9 +501,11 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDftAnaStages; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }   // a K-block = 8 row pairs, one arrival each
     for (int b = 0; b < 4; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int s = 0; s < p.nraw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
     mbar_init(b_full, 1);
     fence_barrier_init();
     prefetch_tmap(&p.tmB);
+    prefetch_tmap(&p.tmX);
   }
   if (warp == 4) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -517,7 +529,7 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
         const uint32_t d = tmem + buf * 64;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
-          mbar_wait(&full[s], it & 1);   // precise wake-up: the stage is released (empty) only after these MMAs, and the ring is one tile deep
+          mbar_wait(&full[s], it & 1);   // precise wake-up: the stage is released (empty) only after these MMAs
           tc_fence_after();
           const uint32_t st = sAr + s * 65536;
           const uint32_t bc = sBm + kb * 8192, bs = bc + 4096;
@@ -532,6 +544,26 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------------------------- sample loader
+    if (lane == 0) {
+      int n = 0;
+      for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+        const int r = ti / p.ktiles, row0 = r * p.nlat + (ti - r * p.ktiles) * 16;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int g = n * nkb + kb, rs = g % p.nraw, it = g / p.nraw;
+          if (it > 0) mbar_wait(&raw_empty[rs], (it - 1) & 1);
+          mbar_expect_tx(&raw_full[rs], kRawBytes);
+          const uint32_t dst = sRaw + rs * kRawBytes;
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) {
+            tma_load_2d(dst + (2 * j1) * (16 * 32 * sizeof(T)), &p.tmX, &raw_full[rs], N2 * j1 + 32 * kb, row0);                  // columns j2
+            tma_load_2d(dst + (2 * j1 + 1) * (16 * 32 * sizeof(T)), &p.tmX, &raw_full[rs], N2 * j1 + N2 - 32 * kb - 31, row0);    // partners N2 - j2 (reversed)
+          }
+        }
       }
     }
     __syncwarp();
@@ -574,91 +606,60 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
     }
   } else {
     // ------------------------------------------------------------------------------------------- producers
-    // Warp = (K-block kb, slot): lanes are 32 consecutive columns j2 of K-block kb; the warp walks the rows slot, slot + nslots, ...
-    // of every tile.  Per row ("item") a lane loads its column and the partner column N2 - j2 (8 samples each, 64-byte runs per warp
-    // instruction), runs both radix-8 butterflies + twiddles and stores Ye = Y'(j2) + Y'(N2-j2), Yo = Y'(j2) - Y'(N2-j2) for the
-    // 8 classes into the four K-major operand planes (one 128-byte row per warp store: conflict free).
-    // Latency: the samples of the NEXT item are in flight (registers) while the current one is computed, and the rows of the tile
-    // after next are pulled into L2 by one prefetch per thread.  Lanes beyond N2/2 and rows beyond nlat carry zeros.
-    const int pw = warp - 5;
-    const int nprod = (int)(blockDim.x >> 5) - 5;  // producer warps: 12 (three K-blocks) or 8
-    const int N2 = N2T > 0 ? N2T : p.N2;
-    const int nlon = 8 * N2;
-    // Work item = (K-block kb, row pair q): lanes are the 32 columns j2 of K-block kb, rows 2q and 2q + 1 of the tile travel in the two
-    // halves of packed f32x2 registers.  Items are taken in K-block-major order (item = kb * 8 + q; warp w does w, w + nprod, ...), so the
-    // first K-block of a tile is complete -- and its MMAs run -- while the warps are still producing the later ones, and the next tile's
-    // first K-block never waits for the tensor core (with one K-block per warp the producers idled ~15 % of the tile behind the MMAs).
-    const int items = 8 * nkb, ipw = items / nprod;
-    const T* const x = static_cast<const T*>(p.x);
-    const T* const zp = static_cast<const T*>(p.zeros);
+    // warp pw owns row pair q = pw of EVERY K-block of a tile (rows 2q, 2q + 1 in the halves of packed f32x2 registers); lanes = the 32 columns
+    // of the K-block.  K-blocks are produced in order, so the MMAs of K-block kb run while the warps work on kb + 1.
+    const int q = warp - 6;
     constexpr bool kBf16 = (sizeof(T) == 2);
-    // tiles of this CTA: blockIdx.x, + gridDim.x, ...  as (image r, row tile kt), advanced without divisions
-    const int dq = gridDim.x / p.ktiles, dr = gridDim.x - dq * p.ktiles;
-    auto advance = [&](int& r, int& kt) {
-      kt += dr; r += dq;
-      if (kt >= p.ktiles) { kt -= p.ktiles; ++r; }
-    };
-    // eight samples of column j2 (or of its partner N2 - j2) of the two rows of an item: raw[0..7] row 0, raw[8..15] row 1.
-    // Unconditional loads: lanes / rows without a sample read a page of zeros.
-    auto load_col = [&](uint32_t* raw, int r, int kt, int item, bool partner) {
-      const int kb = item >> 3, k0 = kt * 16 + 2 * (item & 7);
-      const int j2 = 32 * kb + lane;
-      const bool valid = j2 <= p.half;
-      const bool use = partner ? (valid && j2 != 0 && 2 * j2 != N2) : valid;
-      const int jj = partner ? N2 - j2 : j2;
-      const bool ok0 = use && r < p.R && k0 < p.nlat, ok1 = use && r < p.R && k0 + 1 < p.nlat;
-      const T* p0 = ok0 ? x + ((size_t)r * p.nlat + k0) * nlon + jj : zp;
-      const T* p1 = ok1 ? p0 + nlon : zp;
+    const T* const rawS = reinterpret_cast<const T*>(gR);
+    int n = 0;
+    for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
+      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16 + 2 * q;
+      const bool row0ok = k0 < p.nlat, row1ok = k0 + 1 < p.nlat;   // rows beyond nlat belong to the next image (or are out of bounds): treated as zeros
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int g = n * nkb + kb;
+        const int j2 = 32 * kb + lane;
+        const bool valid = j2 <= p.half;
+        const bool paired = valid && j2 != 0 && 2 * j2 != N2;
+        const int rs = g % p.nraw;
+        mbar_wait(&raw_full[rs], (g / p.nraw) & 1);
+        const T* const rb = rawS + (size_t)rs * (kRawBytes / sizeof(T)) + (2 * q) * 32;
+        pr xa[8], xb[8];
 #pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) raw[j1] = ld_raw<T>(p0 + N2 * j1);
-#pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) raw[8 + j1] = ld_raw<T>(p1 + N2 * j1);
-    };
-    auto unpack = [&](const uint32_t* raw, pr* xv) {
-#pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1)
-        xv[j1] = make_pr(__uint_as_float(kBf16 ? raw[j1] << 16 : raw[j1]), __uint_as_float(kBf16 ? raw[8 + j1] << 16 : raw[8 + j1]));
-    };
-    uint32_t rawA[16], rawB[16];
-    int r = blockIdx.x / p.ktiles, kt = blockIdx.x - r * p.ktiles;
-    load_col(rawA, r, kt, pw, false);
-    for (int n = 0; r < p.R; ++n) {
-      int rn = r, ktn = kt;
-      advance(rn, ktn);
-      {  // L2 prefetch of the tile after next (its samples are first touched ~2 tile times from now)
-        int r2 = rn, kt2 = ktn;
-        advance(r2, kt2);
-        if (r2 < p.R) {
-          const int k2 = kt2 * 16;
-          const int rows = p.nlat - k2 < 16 ? p.nlat - k2 : 16;
-          const char* b2 = reinterpret_cast<const char*>(x + ((size_t)r2 * p.nlat + k2) * nlon);
-          const int lines = (int)(((size_t)rows * nlon * sizeof(T) + 127) >> 7);
-          for (int l = pw * 32 + lane; l < lines; l += nprod * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (size_t)l * 128));
+        for (int j1 = 0; j1 < 8; ++j1) {
+          // box (2 j1): [16 rows][32 columns]; box (2 j1 + 1): partner columns in reversed order (column 31 - lane)
+          const T* b0 = rb + (2 * j1) * (16 * 32);
+          const T* b1 = rb + (2 * j1 + 1) * (16 * 32);
+          float a0, a1, c0, c1;
+          if constexpr (kBf16) {
+            a0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[lane] << 16);
+            a1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[32 + lane] << 16);
+            c0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[31 - lane] << 16);
+            c1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[32 + 31 - lane] << 16);
+          } else {
+            a0 = reinterpret_cast<const float*>(b0)[lane];
+            a1 = reinterpret_cast<const float*>(b0)[32 + lane];
+            c0 = reinterpret_cast<const float*>(b1)[31 - lane];
+            c1 = reinterpret_cast<const float*>(b1)[32 + 31 - lane];
+          }
+          xa[j1] = make_pr((valid && row0ok) ? a0 : 0.f, (valid && row1ok) ? a1 : 0.f);
+          xb[j1] = make_pr((paired && row0ok) ? c0 : 0.f, (paired && row1ok) ? c1 : 0.f);
         }
-      }
-      for (int ii = 0; ii < ipw; ++ii) {
-        const int item = pw + ii * nprod;
-        const int kb = item >> 3, q = item & 7;
-        load_col(rawB, r, kt, item, true);              // partner column: in flight during the first butterfly
-        pr xv[8], er[8], ei[8], br[8], bi[8];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);   // samples are in registers: the raw stage may be refilled
+        pr er[8], ei[8], br[8], bi[8];
         float2 tw[8], tp[8];
         tw[0] = make_float2(1.f, 0.f);
         const float2* const twl = twS + kb * 224 + lane;   // tw[c] = twl[(c - 1) * 32], already scaled for the truncation compensation
 #pragma unroll
         for (int c = 1; c < 8; ++c) tw[c] = twl[(c - 1) * 32];
-        unpack(rawA, xv);
-        dft_ana_radix8<pr>(xv, tw, er, ei);
         dft_partner_twiddles(tw, tp);   // products of the tw components with constants of modulus 1: they carry the (1 + f) factor too
-        unpack(rawB, xv);
-        dft_ana_radix8<pr>(xv, tp, br, bi);
-        if (ii + 1 < ipw) load_col(rawA, r, kt, item + nprod, false);   // next item's first column: in flight during the stores
-        else load_col(rawA, rn, ktn, pw, false);
-        const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
+        dft_ana_radix8<pr>(xa, tw, er, ei);
+        dft_ana_radix8<pr>(xb, tp, br, bi);
+        const int s = g % kDftAnaStages, it = g / kDftAnaStages;
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
         float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
         const int kr0 = 2 * q;
-        // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8);
-        // kr0 is even, so the second row is the next 128-byte line with the XOR term differing in bit 0
+        // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8)
         float* const d0 = stg + kr0 * 32 + ((((lane >> 2) ^ (kr0 & 7)) << 2) | (lane & 3));
         float* const d1 = stg + (kr0 + 1) * 32 + ((((lane >> 2) ^ ((kr0 + 1) & 7)) << 2) | (lane & 3));
 #pragma unroll
@@ -680,7 +681,6 @@ __global__ void __launch_bounds__(544, 1) dft_analysis_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
       }
-      r = rn; kt = ktn;
     }
   }
   tc_fence_before();
@@ -694,12 +694,12 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const int R = B * C;
   DftAnaParams p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.zeros = t->zeros;
+  p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale;
   p.R = R; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
   p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
-  const int pwarps = (t->nkb == 3) ? 12 : 8;
-  p.nslots = pwarps / t->nkb;
+  const bool bf16 = (dtype == B200SHT_BF16);
+  p.nraw = bf16 ? 4 : 2;   // raw stages of 16 / 32 KB
   p.idesc = make_idesc(32, 0, 0, 0);
   p.idesc_neg = make_idesc(32, 0, 0, 1);
   {
@@ -708,10 +708,15 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
     int rc = make_tmap(&p.tmB, t->eb, 2, d, s, bx);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + 256 + (size_t)t->nkb * 7 * 32 * 8;
+  {
+    int rc = make_tmap_rows(&p.tmX, x, bf16, pl->nlon, (long long)R * pl->nlat, 32, 16);
+    if (rc) return rc;
+  }
+  const size_t raw_bytes = (size_t)16 * 16 * 32 * (bf16 ? 2 : 4);
+  const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + p.nraw * raw_bytes + 3 * 7 * 32 * 8 + 256;
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
-  const int threads = 32 * (5 + pwarps);
+  const int threads = 32 * (6 + 8);
 #define B200_LAUNCH_ANA(TT, NN)                                                                                                          \
   do {                                                                                                                                  \
     B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
@@ -724,7 +729,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
     case 60: B200_LAUNCH_ANA(TT, 60); break;   /* nlon  480 */           \
     default: B200_LAUNCH_ANA(TT, 0); break;                              \
   }
-  if (dtype == B200SHT_BF16) { B200_DISPATCH_ANA(__nv_bfloat16) } else { B200_DISPATCH_ANA(float) }
+  if (bf16) { B200_DISPATCH_ANA(__nv_bfloat16) } else { B200_DISPATCH_ANA(float) }
 #undef B200_DISPATCH_ANA
 #undef B200_LAUNCH_ANA
   B200_CHECK_LAUNCH();

@@ -212,4 +212,23 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
 }
 
 
+// 2-D tensor map over a row-major matrix of fp32 or bf16 elements without swizzle: box rows land densely (box_cols * esize bytes apart)
+inline int make_tmap_rows(CUtensorMap* tm, const void* base, bool bf16, long long cols, long long rows, int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const int es = bf16 ? 2 : 4;
+  cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)cols * es};
+  cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, el[2] = {1, 1};
+  if (gs[0] % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (box_cols * es) % 16 != 0) {
+    set_error("tensor map (rows): base / row pitch / box row not 16-byte aligned");
+    return B200SHT_ERR_INVALID;
+  }
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gd, gs, bx, el,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (rows) failed (%d)", (int)r); return B200SHT_ERR_CUDA; }
+  return 0;
+}
+
 }  // namespace b200sht
