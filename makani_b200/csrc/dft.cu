@@ -448,7 +448,8 @@ constexpr int kDftAnaStages = 2;   // operand ring: one stage = one K-block (32 
 
 struct DftAnaParams {
   alignas(64) CUtensorMap tmB;   // E tiles (32 j2 local, nkb * 64 rows), box (32, 32): K-major B operand
-  alignas(64) CUtensorMap tmX;   // the input as a matrix [R * nlat rows][nlon], box (32 columns, 16 rows), no swizzle
+  alignas(64) CUtensorMap tmXc;  // the input as a matrix [R * nlat rows][nlon], box (Wc columns, 16 rows), no swizzle: columns j2
+  alignas(64) CUtensorMap tmXp;  // same, box (Wp columns, 16 rows): partner columns N2 - j2
   float* X;
   const float2* tw;
   const float* rowscale;
@@ -471,7 +472,13 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  constexpr uint32_t kRawBytes = 16u * 16u * 32u * sizeof(T);   // 16 boxes x 16 rows x 32 columns
+  // TMA needs 16-byte aligned box starts (found on the GPU: an unaligned inner coordinate is an illegal instruction): a box starts at the
+  // column rounded down to kAl elements and is wide enough to still contain the 32 wanted ones.  fp32 column boxes are exact (N2 % 4 == 0 is
+  // required by the host for fp32 input).
+  constexpr int kAl = 16 / (int)sizeof(T);                       // 8 (bf16) / 4 (fp32)
+  constexpr int kWc = (sizeof(T) == 2) ? 40 : 32, kWp = (sizeof(T) == 2) ? 40 : 36;
+  constexpr uint32_t kColBytes = 16u * kWc * sizeof(T), kParBytes = 16u * kWp * sizeof(T);   // one box: 16 rows
+  constexpr uint32_t kRawBytes = 8u * (kColBytes + kParBytes);
   const uint32_t oB = 0, oA = 3 * 8192, oR = oA + kDftAnaStages * 65536, oT = oR + (uint32_t)p.nraw * kRawBytes, oBar = oT + 3 * 7 * 32 * 8;
   const uint32_t sBm = base + oB, sAr = base + oA, sRaw = base + oR;
   uint8_t* gA = gbase + oA;
@@ -505,7 +512,8 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     mbar_init(b_full, 1);
     fence_barrier_init();
     prefetch_tmap(&p.tmB);
-    prefetch_tmap(&p.tmX);
+    prefetch_tmap(&p.tmXc);
+    prefetch_tmap(&p.tmXp);
   }
   if (warp == 4) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -560,8 +568,9 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
           const uint32_t dst = sRaw + rs * kRawBytes;
 #pragma unroll
           for (int j1 = 0; j1 < 8; ++j1) {
-            tma_load_2d(dst + (2 * j1) * (16 * 32 * sizeof(T)), &p.tmX, &raw_full[rs], N2 * j1 + 32 * kb, row0);                  // columns j2
-            tma_load_2d(dst + (2 * j1 + 1) * (16 * 32 * sizeof(T)), &p.tmX, &raw_full[rs], N2 * j1 + N2 - 32 * kb - 31, row0);    // partners N2 - j2 (reversed)
+            const int sc = N2 * j1 + 32 * kb, sp = N2 * j1 + N2 - 32 * kb - 31;   // first wanted column / partner column (sp < 0 only for N2 < 31)
+            tma_load_2d(dst + j1 * kColBytes, &p.tmXc, &raw_full[rs], (sc / kAl) * kAl, row0);
+            tma_load_2d(dst + 8 * kColBytes + j1 * kParBytes, &p.tmXp, &raw_full[rs], sp < 0 ? 0 : (sp / kAl) * kAl, row0);
           }
         }
       }
@@ -622,24 +631,28 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
         const bool paired = valid && j2 != 0 && 2 * j2 != N2;
         const int rs = g % p.nraw;
         mbar_wait(&raw_full[rs], (g / p.nraw) & 1);
-        const T* const rb = rawS + (size_t)rs * (kRawBytes / sizeof(T)) + (2 * q) * 32;
+        const T* const rb = rawS + (size_t)rs * (kRawBytes / sizeof(T));
         pr xa[8], xb[8];
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
-          // box (2 j1): [16 rows][32 columns]; box (2 j1 + 1): partner columns in reversed order (column 31 - lane)
-          const T* b0 = rb + (2 * j1) * (16 * 32);
-          const T* b1 = rb + (2 * j1 + 1) * (16 * 32);
+          // column box j1: [16 rows][kWc]; partner box j1: [16 rows][kWp]; both start at the wanted column rounded down to kAl
+          const int sc = N2 * j1 + 32 * kb, sp = N2 * j1 + N2 - 32 * kb - 31;
+          const int ic = sc - (sc / kAl) * kAl + lane;                          // column j2 = 32 kb + lane
+          int ip = N2 * j1 + N2 - j2 - (sp < 0 ? 0 : (sp / kAl) * kAl);          // column N2 - j2
+          ip = ip < 0 ? 0 : (ip > kWp - 1 ? kWp - 1 : ip);                      // lanes without a partner read anything inside the box
+          const T* b0 = rb + j1 * (16 * kWc) + (2 * q) * kWc;
+          const T* b1 = rb + 8 * (16 * kWc) + j1 * (16 * kWp) + (2 * q) * kWp;
           float a0, a1, c0, c1;
           if constexpr (kBf16) {
-            a0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[lane] << 16);
-            a1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[32 + lane] << 16);
-            c0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[31 - lane] << 16);
-            c1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[32 + 31 - lane] << 16);
+            a0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[ic] << 16);
+            a1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[kWc + ic] << 16);
+            c0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[ip] << 16);
+            c1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[kWp + ip] << 16);
           } else {
-            a0 = reinterpret_cast<const float*>(b0)[lane];
-            a1 = reinterpret_cast<const float*>(b0)[32 + lane];
-            c0 = reinterpret_cast<const float*>(b1)[31 - lane];
-            c1 = reinterpret_cast<const float*>(b1)[32 + 31 - lane];
+            a0 = reinterpret_cast<const float*>(b0)[ic];
+            a1 = reinterpret_cast<const float*>(b0)[kWc + ic];
+            c0 = reinterpret_cast<const float*>(b1)[ip];
+            c1 = reinterpret_cast<const float*>(b1)[kWp + ip];
           }
           xa[j1] = make_pr((valid && row0ok) ? a0 : 0.f, (valid && row1ok) ? a1 : 0.f);
           xb[j1] = make_pr((paired && row0ok) ? c0 : 0.f, (paired && row1ok) ? c1 : 0.f);
@@ -699,7 +712,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
   p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
   const bool bf16 = (dtype == B200SHT_BF16);
-  p.nraw = bf16 ? 4 : 2;   // raw stages of 16 / 32 KB
+  p.nraw = bf16 ? 3 : 2;   // raw stages of 20 / 34 KB
   p.idesc = make_idesc(32, 0, 0, 0);
   p.idesc_neg = make_idesc(32, 0, 0, 1);
   {
@@ -708,11 +721,13 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
     int rc = make_tmap(&p.tmB, t->eb, 2, d, s, bx);
     if (rc) return rc;
   }
+  B200_REQUIRE(bf16 || t->N2 % 4 == 0, "dft_analysis: fp32 input needs nlon %% 32 == 0 (16-byte aligned TMA boxes)");
   {
-    int rc = make_tmap_rows(&p.tmX, x, bf16, pl->nlon, (long long)R * pl->nlat, 32, 16);
+    int rc = make_tmap_rows(&p.tmXc, x, bf16, pl->nlon, (long long)R * pl->nlat, bf16 ? 40 : 32, 16);
+    if (!rc) rc = make_tmap_rows(&p.tmXp, x, bf16, pl->nlon, (long long)R * pl->nlat, bf16 ? 40 : 36, 16);
     if (rc) return rc;
   }
-  const size_t raw_bytes = (size_t)16 * 16 * 32 * (bf16 ? 2 : 4);
+  const size_t raw_bytes = bf16 ? (size_t)8 * 16 * (40 + 40) * 2 : (size_t)8 * 16 * (32 + 36) * 4;
   const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + p.nraw * raw_bytes + 3 * 7 * 32 * 8 + 256;
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;

@@ -852,7 +852,9 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
 int fft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int scale_mode, cudaStream_t st) {
   B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "fft_analysis: B*C=%lld out of range", (long long)B * C);
   B200_REQUIRE(dtype == B200SHT_F32 || dtype == B200SHT_BF16, "fft_analysis: unknown dtype %d", dtype);
-  if ((scale_mode & 2) && dft_usable(pl)) return dft_analysis(pl, x, dtype, B, C, X, scale_mode & 1, 1, st);
+  // tensor-core DFT: TMA reads the samples, so the input must be 16-byte aligned (and nlon % 32 == 0 for fp32 input); otherwise the CUDA-core FFT
+  if ((scale_mode & 2) && dft_usable(pl) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (dtype == B200SHT_BF16 || pl->nlon % 32 == 0))
+    return dft_analysis(pl, x, dtype, B, C, X, scale_mode & 1, 1, st);
   FftParams prm = make_params(pl, B, C, scale_mode, nullptr);
   if (dtype == B200SHT_F32) return run_fft_dir<float>(pl, 0, x, X, prm, st);
   if (dtype == B200SHT_BF16) return run_fft_dir<__nv_bfloat16>(pl, 0, x, X, prm, st);
