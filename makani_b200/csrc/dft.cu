@@ -615,16 +615,23 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     }
   } else {
     // ------------------------------------------------------------------------------------------- producers
-    // warp pw owns row pair q = pw of EVERY K-block of a tile (rows 2q, 2q + 1 in the halves of packed f32x2 registers); lanes = the 32 columns
-    // of the K-block.  K-blocks are produced in order, so the MMAs of K-block kb run while the warps work on kb + 1.
-    const int q = warp - 6;
+    // Work item = (K-block kb, row pair q): rows 2q, 2q + 1 of the tile in the halves of packed f32x2 registers, lanes = the 32 columns of the
+    // K-block.  Items are taken in K-block-major order (item = kb * 8 + q; warp w does w, w + nprod, ...): the MMAs of K-block kb run while
+    // the warps work on kb + 1.  12 producer warps for three K-blocks (2 items per warp and tile), 8 otherwise: the kernel is bound by the
+    // latency of the dependent butterfly chains, so the tile time is (items per warp) x (item latency).
+    const int pw = warp - 6;
+    const int nprod = (int)(blockDim.x >> 5) - 6;
+    const int ipw = (8 * nkb) / nprod;
     constexpr bool kBf16 = (sizeof(T) == 2);
     const T* const rawS = reinterpret_cast<const T*>(gR);
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16 + 2 * q;
-      const bool row0ok = k0 < p.nlat, row1ok = k0 + 1 < p.nlat;   // rows beyond nlat belong to the next image (or are out of bounds): treated as zeros
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int r = ti / p.ktiles, kt16 = (ti - r * p.ktiles) * 16;
+      for (int ii = 0; ii < ipw; ++ii) {
+        const int item = pw + ii * nprod;
+        const int kb = item >> 3, q = item & 7;
+        const int k0 = kt16 + 2 * q;
+        const bool row0ok = k0 < p.nlat, row1ok = k0 + 1 < p.nlat;   // rows beyond nlat belong to the next image (or are out of bounds): treated as zeros
         const int g = n * nkb + kb;
         const int j2 = 32 * kb + lane;
         const bool valid = j2 <= p.half;
@@ -731,7 +738,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + p.nraw * raw_bytes + 3 * 7 * 32 * 8 + 256;
   const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
-  const int threads = 32 * (6 + 8);
+  const int threads = 32 * (6 + (t->nkb == 3 ? 12 : 8));
 #define B200_LAUNCH_ANA(TT, NN)                                                                                                          \
   do {                                                                                                                                  \
     B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
