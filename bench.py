@@ -623,12 +623,16 @@ def run_gpu_arm(args):
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            fam = {"fft_analysis": "fft_analysis_ct_kernel", "fft_synthesis": "fft_synthesis_ct_kernel", "legendre_analysis": "umma_kernel<AnaTraits>",
-                   "legendre_synthesis": "umma_kernel<SynTraits>", "mix_forward": "umma_kernel<MixFwdTraits>", "mix_backward": "umma_kernel<MixDgradTraits>"}
-            key = next((v for k, v in fam.items() if top.startswith(k)), None)
-            for name, rec in tj.items():
-                if key and key in name:
-                    traffic = rec["dram_bytes_per_launch"]
+            fam = {"fft_analysis": ("dft_analysis_kernel", "fft_analysis_ct_kernel"), "fft_synthesis": ("dft_synthesis_kernel", "fft_synthesis_ct_kernel"),
+                   "legendre_analysis": ("umma_kernel<AnaTraits>",), "legendre_synthesis": ("umma_kernel<SynTraits>",),
+                   "mix_forward": ("umma_kernel<MixFwdTraits>",), "mix_backward": ("umma_kernel<MixDgradTraits>",)}
+            keys = next((v for k, v in fam.items() if top.startswith(k)), ())
+            for key in keys:   # only a capture of THIS workload says anything about this launch's traffic
+                for name, rec in tj.items():
+                    if key in name and rec.get("workload") == wl:
+                        traffic = rec["dram_bytes_per_launch"]
+                        break
+                if traffic is not None:
                     break
         except Exception:
             traffic = None

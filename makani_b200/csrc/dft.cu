@@ -36,7 +36,7 @@ struct DftTables {
   float* et;      // synthesis A: [2][128 rows = lane -> j2][32 m2]  (cos, sin), TF32-rounded
   float* eb;      // analysis  B: [nkb][2][32 rows m2][32 j2 local]  (cos, sin), TF32-rounded
   float2* tw;     // [8][N2]  exp(+2 pi i c j2 / nlon)
-  float* trash;   // 64 x 4 * nlon floats: store target of the synthesis rows / lanes without output (keeps the stores unconditional); one slab per CTA % 64
+  float* trash;   // 64 x (4 * nlon + 256) floats: store target of the synthesis rows / lanes without output (keeps the stores unconditional); one slab per CTA % 64
   float* zeros;   // 8 * N2 floats of zeros: load target of the analysis lanes / rows that carry no sample (keeps the loads unconditional)
   int N2, half, M2, qpr, nrep, nkb;
 };
@@ -95,7 +95,7 @@ int dft_plan_init(Plan* pl) {
   if (e == cudaSuccess) e = cudaMalloc(&t->tw, sizeof(float2) * 8 * t->N2);
   if (e == cudaSuccess) e = cudaMalloc(&t->zeros, sizeof(float) * 8 * t->N2);
   if (e == cudaSuccess) e = cudaMemset(t->zeros, 0, sizeof(float) * 8 * t->N2);
-  if (e == cudaSuccess) e = cudaMalloc(&t->trash, sizeof(float) * 64 * 4 * pl->nlon);
+  if (e == cudaSuccess) e = cudaMalloc(&t->trash, sizeof(float) * 64 * (4 * (size_t)pl->nlon + 256));   // + 256: idle lanes index up to j2 = 127 + 7 N2 past a row
   if (e == cudaSuccess) {
     const int n = 8192 > 8 * t->N2 ? 8192 : 8 * t->N2;
     dft_tables_kernel<<<(n + 255) / 256, 256>>>(t->et, t->eb, t->tw, t->N2, t->half, t->M2, t->qpr, t->nrep, t->nkb, pl->nlon);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
     T* const y = static_cast<T*>(p.y);
     const float smul = p.mode == 0 ? 2.f : 1.f;
     const int nyq_m = nlon / 2;
-    T* const trash = static_cast<T*>(p.trash) + (size_t)(blockIdx.x & 63) * 4 * nlon;
+    T* const trash = static_cast<T*>(p.trash) + (size_t)(blockIdx.x & 63) * (4 * nlon + 256);
     float2 tw[8], tp[8];
     tw[0] = make_float2(1.f, 0.f);
 #pragma unroll
