@@ -20,42 +20,54 @@ struct MixDims {
 
 // ------------------------------------------------------------------------------------ weight re-layout
 // native DHCONV complex [G][Cig][Cog][L]  <->  packed float [L][G][Cig][2][cop]  (real plane, imaginary plane per input row)
+// A block moves a 128 (o) x 32 (l) tile through shared memory: 16 independent 8-byte loads per thread in flight (the 32 x 32 tiles of
+// round 1 had 4 and ran at 1 TB/s, latency bound: 10 us per re-layout of the 10 MB weight, twice per training step).
+constexpr int kWpO = 128, kWpL = 32;
 __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restrict__ wn, float* __restrict__ wp, int L, int GC /*G*Cig*/, int Cog,
                                                                  int cop, int to_native, int rnd) {
-  __shared__ float2 tile[32][33];
+  __shared__ float2 tile[kWpO][kWpL + 1];
   const int gi = blockIdx.z;
-  const int o0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const int o0 = blockIdx.y * kWpO, l0 = blockIdx.x * kWpL;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (!to_native) {
-    for (int oo = ty; oo < 32; oo += 8) {
-      const int o = o0 + oo, l = l0 + tx;
-      float2 v = make_float2(0.f, 0.f);
-      if (o < Cog && l < L) v = wn[((size_t)gi * Cog + o) * L + l];
-      tile[oo][tx] = v;
+    float2 v[kWpO / 8];
+#pragma unroll
+    for (int i = 0; i < kWpO / 8; ++i) {
+      const int o = o0 + ty + 8 * i, l = l0 + tx;
+      v[i] = (o < Cog && l < L) ? wn[((size_t)gi * Cog + o) * L + l] : make_float2(0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < kWpO / 8; ++i) tile[ty + 8 * i][tx] = v[i];
     __syncthreads();
-    for (int ll = ty; ll < 32; ll += 8) {
-      const int l = l0 + ll, o = o0 + tx;
-      if (l < L && o < cop) {
-        float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
-        row[o] = rnd ? tf32_rn(tile[tx][ll].x) : tile[tx][ll].x;
-        row[cop + o] = rnd ? tf32_rn(tile[tx][ll].y) : tile[tx][ll].y;
+    for (int ll = ty; ll < kWpL; ll += 8) {
+      const int l = l0 + ll;
+      if (l >= L) continue;
+      float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
+#pragma unroll
+      for (int oo = 0; oo < kWpO; oo += 32) {
+        const int o = o0 + oo + tx;
+        if (o < cop) {
+          const float2 t = tile[oo + tx][ll];
+          row[o] = rnd ? tf32_rn(t.x) : t.x;
+          row[cop + o] = rnd ? tf32_rn(t.y) : t.y;
+        }
       }
     }
   } else {
-    for (int ll = ty; ll < 32; ll += 8) {
-      const int l = l0 + ll, o = o0 + tx;
-      float2 v = make_float2(0.f, 0.f);
-      if (l < L && o < cop) {
-        const float* row = wp + ((size_t)l * GC + gi) * 2 * cop;
-        v = make_float2(row[o], row[cop + o]);
+    for (int ll = ty; ll < kWpL; ll += 8) {
+      const int l = l0 + ll;
+      const float* row = wp + ((size_t)(l < L ? l : 0) * GC + gi) * 2 * cop;
+#pragma unroll
+      for (int oo = 0; oo < kWpO; oo += 32) {
+        const int o = o0 + oo + tx;
+        tile[oo + tx][ll] = (l < L && o < cop) ? make_float2(row[o], row[cop + o]) : make_float2(0.f, 0.f);
       }
-      tile[tx][ll] = v;
     }
     __syncthreads();
-    for (int oo = ty; oo < 32; oo += 8) {
-      const int o = o0 + oo, l = l0 + tx;
-      if (o < Cog && l < L) wn[((size_t)gi * Cog + o) * L + l] = tile[oo][tx];
+#pragma unroll
+    for (int i = 0; i < kWpO / 8; ++i) {
+      const int o = o0 + ty + 8 * i, l = l0 + tx;
+      if (o < Cog && l < L) wn[((size_t)gi * Cog + o) * L + l] = tile[ty + 8 * i][tx];
     }
   }
 }
@@ -80,7 +92,7 @@ int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, in
   B200_REQUIRE(G > 0 && Ci % G == 0 && Co % G == 0, "mix_weight: channels (%d,%d) not divisible by groups %d", Ci, Co, G);
   const int Cig = Ci / G, Cog = Co / G, cop = round_up(Cog, 4);
   if (op == B200SHT_OP_DHCONV) {
-    dim3 grid(ceil_div(L, 32), ceil_div(cop, 32), G * Cig);
+    dim3 grid(ceil_div(L, kWpL), ceil_div(cop, kWpO), G * Cig);
     B200_REQUIRE(grid.z <= 65535, "mix_weight: G*Cig=%u exceeds grid limit", grid.z);
     weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop, to_native, round_tf32);
   } else if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) {
