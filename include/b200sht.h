@@ -226,6 +226,9 @@ int b200sht_debug_fft_host(int N, int mmax, int direction, const float* in_a, co
  * GEMM summed in double on the host.  direction 0: in float[N] -> out float[2*mmax] (interleaved); direction 1: the reverse.
  * scale_mode / row_scale as for b200sht_fft_analysis / _synthesis (row_scale = the row's quadrature factor). */
 int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float row_scale, const float* in, float* out);
+/* wait-time profile of the tensor-core DFT kernels (environment B200SHT_DFT_PROF=1): 16 counters of SM clocks, accumulated over all launches since the
+ * last call and cleared by it (slots: see csrc/dft.cu).  All zeros when the profile is off.  Synchronises the device. */
+int b200sht_debug_dft_profile(uint64_t* counters16);
 /* radices chosen for length N; returns the number of stages or a negative status */
 int b200sht_debug_fft_plan(int N, int* radices, int max_radices);
 /* table [mmax][lmax][nlat] (fp32) from cos(colatitude) cost[nlat] */

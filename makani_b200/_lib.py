@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sht.so")
+# B200SHT_LIBRARY: another build of the same library (e.g. the wait-profile build of scripts/dft_waitprof.py); default: the in-tree one
+LIB_PATH = os.environ.get("B200SHT_LIBRARY") or os.path.join(_HERE, "libb200sht.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "b200sht.h")
 
 F32, BF16 = 0, 1
@@ -71,6 +72,7 @@ _SIGNATURES = {
     # debug / CPU-testable entry points (same device code compiled for the host)
     "b200sht_debug_fft_host": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "b200sht_debug_dft_host": (c_int, [c_int, c_int, c_int, c_int, c_float, _P, _P]),
+    "b200sht_debug_dft_profile": (c_int, [_P]),
     "b200sht_debug_fft_plan": (c_int, [c_int, _P, c_int]),
     "b200sht_debug_table_host": (c_int, [c_int, c_int, c_int, _P, c_int, _P]),
 }

@@ -17,8 +17,10 @@ def _newer(a, b):
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
-def build(force=False, verbose=False):
-    objdir = os.path.join(HERE, "build")
+def build(force=False, verbose=False, defines=(), out=OUT):
+    """defines: extra -D macros (a separate object directory and output file per variant, e.g. the profile build
+    `build(defines=["B200SHT_DFT_PROFILE"], out=.../libb200sht_prof.so)`)."""
+    objdir = os.path.join(HERE, "build" + ("_" + "_".join(defines) if defines else ""))
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "b200sht.h"))
@@ -31,7 +33,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(objdir, os.path.basename(obj) + ".log")
         with open(log, "w") as f:
@@ -45,13 +47,19 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=6) as ex:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or not os.path.exists(OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart", "-lcuda"]
+    if force or jobs or not os.path.exists(out):
+        cmd = [NVCC, "-shared", "-o", out] + objs + ["-lcudart", "-lcuda"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--define" in sys.argv:    # experiment builds: --define MACRO --out name.so
+        d = sys.argv[sys.argv.index("--define") + 1]
+        print(build(defines=d.split(","), out=os.path.join(HERE, sys.argv[sys.argv.index("--out") + 1])))
+    elif "--profile" in sys.argv:   # wait-time counters in the DFT kernels (scripts/dft_waitprof.py); not the shipped build
+        print(build(force="--force" in sys.argv, defines=["B200SHT_DFT_PROFILE"], out=os.path.join(HERE, "libb200sht_prof.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

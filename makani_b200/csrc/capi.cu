@@ -42,6 +42,7 @@ void umma_plan_destroy(Plan* pl);
 int dft_plan_init(Plan* pl);
 void dft_plan_destroy(Plan* pl);
 int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out);
+int dft_profile_read(unsigned long long* out16);
 int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
 int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st);
 bool dft_usable(const Plan* pl);
@@ -517,6 +518,11 @@ int b200sht_spectral_conv_forward_host(const b200sht_plan* f, const b200sht_plan
     return B200SHT_ERR_CUDA;
   }
   return rc;
+}
+
+int b200sht_debug_dft_profile(uint64_t* counters16) {
+  B200_REQUIRE(counters16 != nullptr, "debug_dft_profile: null argument");
+  return dft_profile_read(reinterpret_cast<unsigned long long*>(counters16));
 }
 
 int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float row_scale, const float* in, float* out) {

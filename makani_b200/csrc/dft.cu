@@ -69,6 +69,7 @@ __global__ void dft_tables_kernel(float* et, float* eb, float2* tw, int N2, int 
       const long long t = ((long long)m2 * j2) % N2;
       const double ang = 2.0 * M_PI * (double)t / (double)N2;
       v = tf32_rn((float)(p == 0 ? cos(ang) : sin(ang)));
+      if (2 * j2 == N2) v *= 0.5f;   // the column N2 / 2 is its own partner: the producers count it twice (no mask)
     }
     eb[i] = v;
   }
@@ -124,6 +125,40 @@ static bool dft_enabled() {
   return on != 0;
 }
 bool dft_usable(const Plan* pl) { return pl->dft_state != nullptr && dft_enabled(); }
+
+// ----------------------------------------------------------------------------------------- wait-time profile
+// B200SHT_DFT_PROF=1: every role accumulates the SM clocks it spends in its mbarrier waits (one atomic per wait, lane 0 of the warp) into 16
+// counters, read back and cleared by b200sht_debug_dft_profile().  Slots -- analysis: 0 producers / raw samples, 1 producers / operand stage free,
+// 2 loader / raw stage free, 3 MMA / operand stage full, 4 MMA / accumulator free, 5 epilogue / accumulator full, 6 CTA lifetime, 7 producer items;
+// synthesis: 8 TMA / stage free, 9 MMA / stage full, 10 MMA / accumulator free, 11 epilogue / accumulator full, 12 CTA lifetime, 13 epilogue tiles.
+static unsigned long long* g_dft_prof = nullptr;
+static unsigned long long* dft_prof_buffer() {
+  static const int on = [] { const char* e = getenv("B200SHT_DFT_PROF"); return e ? atoi(e) : 0; }();
+  if (!on) return nullptr;
+  if (!g_dft_prof) {
+    if (cudaMalloc(&g_dft_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) { g_dft_prof = nullptr; return nullptr; }
+    cudaMemset(g_dft_prof, 0, 16 * sizeof(unsigned long long));
+  }
+  return g_dft_prof;
+}
+int dft_profile_read(unsigned long long* out16) {
+  if (!g_dft_prof) { for (int i = 0; i < 16; ++i) out16[i] = 0; return 0; }
+  B200_CHECK_CUDA(cudaDeviceSynchronize());
+  B200_CHECK_CUDA(cudaMemcpy(out16, g_dft_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  B200_CHECK_CUDA(cudaMemset(g_dft_prof, 0, 16 * sizeof(unsigned long long)));
+  return 0;
+}
+#ifdef B200SHT_DFT_PROFILE
+constexpr bool kDftProfile = true;
+#else
+constexpr bool kDftProfile = false;   // the counters cost a few instructions per wait: compiled in only by `python -m makani_b200.build --profile`
+#endif
+__device__ __forceinline__ void prof_wait(unsigned long long* prof, int slot, uint64_t* bar, uint32_t parity, bool lead) {
+  if (!kDftProfile || prof == nullptr) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  if (lead) atomicAdd(prof + slot, (unsigned long long)(clock64() - t0));
+}
 
 // ------------------------------------------------------------------------------------------------ small PTX
 __device__ __forceinline__ pr tmem_ld2(uint32_t taddr) {
@@ -205,6 +240,7 @@ struct DftSynParams {
   const float* rowscale;
   const float* bias;
   void* trash;
+  unsigned long long* prof;
   int R, C, nlat, nlon, kp, mmax, N2, half, M2, qpr, nrep, mode, ntiles, ktiles, has_nyq;
   uint32_t idesc;
 };
@@ -213,6 +249,9 @@ struct DftSynParams {
 template <typename T, int N2T>
 __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const __grid_constant__ DftSynParams p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ unsigned long long prof_s[16];   // wait-time profile (B200SHT_DFT_PROF): accumulated per CTA, flushed once at the end
+  unsigned long long* const prof = (kDftProfile && p.prof) ? prof_s : nullptr;
+  if (kDftProfile && threadIdx.x < 16) prof_s[threadIdx.x] = 0;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
@@ -247,6 +286,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const long long t_cta0 = (kDftProfile && p.prof && threadIdx.x == 0) ? clock64() : 0;
 
   if (is_tma) {
     if (lane == 0) {
@@ -256,7 +296,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
         const int s = n % kDftSynStages, it = n / kDftSynStages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        if (it > 0) prof_wait(prof, 8, &empty[s], (it - 1) & 1, true);
         mbar_expect_tx(&full[s], 16384);
         const uint32_t st = sB + s * 16384;
         tma_load_5d(st, &p.tmZ, &full[s], 0, 0, 0, 0, ti);           // re, classes 0..3
@@ -267,29 +307,30 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
     }
     __syncwarp();
   } else if (is_mma) {
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (converged); the MMAs / commits are issued by an elected lane (umma_*_ws)
       mbar_wait(e_full, 0);
+      const uint64_t dE0 = desc_kmajor(sA, 0), dZ0 = desc_mnmajor(sB, 0, 4096);
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
         const int s = n % kDftSynStages, it = n / kDftSynStages;
         const int buf = n & 1, use = n >> 1;
-        if (use > 0) { mbar_wait(&acc_empty[buf], (use - 1) & 1); }
-        mbar_wait(&full[s], it & 1);
+        if (use > 0) { prof_wait(prof, 10, &acc_empty[buf], (use - 1) & 1, lane == 0); }
+        prof_wait(prof, 9, &full[s], it & 1, lane == 0);
         tc_fence_after();
-        const uint32_t st = sB + s * 16384;
+        const uint64_t z0 = desc_advance(dZ0, (uint32_t)s * 16384u);
         const uint32_t d = tmem + buf * 256;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint64_t ac = desc_kmajor(sA, j), as = desc_kmajor(sA + 16384, j);
-          const uint64_t zr = desc_mnmajor(st, j, 4096), zi = desc_mnmajor(st + 8192, j, 4096);
+          const uint64_t ac = desc_advance(dE0, 32 * j), as = desc_advance(dE0, 16384 + 32 * j);
+          const uint64_t zr = desc_advance(z0, 1024 * j), zi = desc_advance(z0, 8192 + 1024 * j);
           const uint32_t acc = j > 0 ? 1u : 0u;
-          umma_tf32(d, ac, zr, p.idesc, acc);          // S1 = cos . Zr
-          umma_tf32(d + 64, as, zi, p.idesc, acc);     // S2 = sin . Zi
-          umma_tf32(d + 128, as, zr, p.idesc, acc);    // S3 = sin . Zr
-          umma_tf32(d + 192, ac, zi, p.idesc, acc);    // S4 = cos . Zi
+          umma_tf32_ws(d, ac, zr, p.idesc, acc);          // S1 = cos . Zr
+          umma_tf32_ws(d + 64, as, zi, p.idesc, acc);     // S2 = sin . Zi
+          umma_tf32_ws(d + 128, as, zr, p.idesc, acc);    // S3 = sin . Zr
+          umma_tf32_ws(d + 192, ac, zi, p.idesc, acc);    // S4 = cos . Zi
         }
-        umma_commit(&empty[s]);
-        umma_commit(&acc_full[buf]);
+        umma_commit_ws(&empty[s]);
+        umma_commit_ws(&acc_full[buf]);
       }
     }
     __syncwarp();
@@ -336,7 +377,8 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
       const pr sc = make_pr(smul * rsa, smul * rsb);
       const pr off_e = make_pr(bias - rsa * (z0a + zna), bias - rsb * (z0b + znb));   // even longitude j
       const pr off_o = make_pr(bias - rsa * (z0a - zna), bias - rsb * (z0b - znb));   // odd longitude j
-      mbar_wait(&acc_full[buf], use & 1);
+      prof_wait(prof, 11, &acc_full[buf], use & 1, lane == 0);
+      if (prof && lane == 0) atomicAdd(prof + 13, 1ull);
       tc_fence_after();
       const uint32_t t0 = tmem + ((uint32_t)(quad * 32) << 16) + buf * 256 + 2 * kpi;
       // rows beyond nlat (last tile of an image) are stored into a scratch row: no predicates / branches around the 32 stores
@@ -391,6 +433,9 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
+  if (kDftProfile && p.prof && threadIdx.x == 0) prof_s[12] = (unsigned long long)(clock64() - t_cta0);
+  if (kDftProfile) __syncthreads();
+  if (kDftProfile && p.prof && threadIdx.x < 16) atomicAdd(p.prof + threadIdx.x, prof_s[threadIdx.x]);
   if (is_mma) tmem_dealloc(tmem, 512);
 }
 
@@ -400,7 +445,7 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   const int R = B * C;
   DftSynParams p;
   memset(&p, 0, sizeof(p));
-  p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias; p.trash = t->trash;
+  p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias; p.trash = t->trash; p.prof = dft_prof_buffer();
   p.R = R; p.C = C; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.qpr = t->qpr; p.nrep = t->nrep; p.mode = mode;
   p.ktiles = pl->kp / 8; p.ntiles = R * p.ktiles;
@@ -444,16 +489,39 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
 }
 
 // ================================================================================================= analysis
+__host__ __device__ constexpr int dft_box_group(int N2, int es) { return (N2 * es) % 16 == 0 ? 1 : (2 * N2 * es) % 16 == 0 ? 2 : (4 * N2 * es) % 16 == 0 ? 4 : 8; }
+
+// 3-D view of the samples for the analysis loader: (column inside a group of gs row segments, group, row), box (box_cols, 8 / gs, 16), no swizzle
+static int make_tmap_segments(CUtensorMap* tm, const void* base, bool bf16, int nlon, int gs, long long rows, int box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const int es = bf16 ? 2 : 4, N2 = nlon / 8;
+  cuuint64_t gd[3] = {(cuuint64_t)gs * N2, (cuuint64_t)(8 / gs), (cuuint64_t)rows};
+  cuuint64_t gst[2] = {(cuuint64_t)gs * N2 * es, (cuuint64_t)nlon * es};
+  cuuint32_t bx[3] = {(cuuint32_t)box_cols, (cuuint32_t)(8 / gs), 16}, el[3] = {1, 1, 1};
+  if (gst[0] % 16 != 0 || gst[1] % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (box_cols * es) % 16 != 0) {
+    set_error("tensor map (segments): base / pitch / box row not 16-byte aligned");
+    return B200SHT_ERR_INVALID;
+  }
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gst, bx, el,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (segments) failed (%d)", (int)r); return B200SHT_ERR_CUDA; }
+  return 0;
+}
+
 constexpr int kDftAnaStages = 2;   // operand ring: one stage = one K-block (32 columns) of a 16-row tile = 4 planes x 16 KB
 
 struct DftAnaParams {
   alignas(64) CUtensorMap tmB;   // E tiles (32 j2 local, nkb * 64 rows), box (32, 32): K-major B operand
-  alignas(64) CUtensorMap tmXc;  // the input as a matrix [R * nlat rows][nlon], box (Wc columns, 16 rows), no swizzle: columns j2
-  alignas(64) CUtensorMap tmXp;  // same, box (Wp columns, 16 rows): partner columns N2 - j2
+  alignas(64) CUtensorMap tmXc;  // the input as [R * nlat rows][8 / gs groups][gs * N2], box (Wc columns, 8 / gs, 16 rows), no swizzle: columns j2
+  alignas(64) CUtensorMap tmXp;  // same, box (Wp columns, 8 / gs, 16 rows): partner columns N2 - j2
   float* X;
   const float2* tw;
   const float* rowscale;
-  int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nraw;
+  unsigned long long* prof;
+  int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nraw, gs;
   uint32_t idesc, idesc_neg;
 };
 
@@ -469,6 +537,9 @@ struct DftAnaParams {
 template <typename T, int N2T>
 __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_constant__ DftAnaParams p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ unsigned long long prof_s[16];   // wait-time profile (B200SHT_DFT_PROF): accumulated per CTA, flushed once at the end
+  unsigned long long* const prof = (kDftProfile && p.prof) ? prof_s : nullptr;
+  if (kDftProfile && threadIdx.x < 16) prof_s[threadIdx.x] = 0;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
@@ -496,6 +567,9 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int nkb = p.nkb;
   const int N2 = N2T > 0 ? N2T : p.N2;
+  // row segments per sample box group: the smallest gs with (gs * N2 elements) a multiple of 16 bytes, so that the segments gm, gm + gs, ...
+  // of all rows form one 3-D TMA box (2 gs boxes per K-block instead of 16)
+  const int gs = N2T > 0 ? dft_box_group(N2T, (int)sizeof(T)) : p.gs;
   for (int i = threadIdx.x; i < nkb * 7 * 32; i += blockDim.x) {
     const int ln = i & 31, c = (i >> 5) % 7 + 1, kb = i / 224;
     const int j2 = 32 * kb + ln;
@@ -515,11 +589,18 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     prefetch_tmap(&p.tmXc);
     prefetch_tmap(&p.tmXp);
   }
+  // imaginary parts of class 0 (rows 0..15 of the planes Ye_i, Yo_i of every operand stage): zero, never written again
+  for (int i = threadIdx.x; i < kDftAnaStages * 2 * 512; i += blockDim.x) {
+    const int st = i >> 10, pl = (i >> 9) & 1, off = i & 511;
+    reinterpret_cast<float*>(gA + (size_t)st * 65536)[(pl ? 12288 : 4096) + off] = 0.f;
+  }
+  fence_proxy_async();
   if (warp == 4) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const long long t_cta0 = (kDftProfile && p.prof && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -528,30 +609,35 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
         tma_load_2d(sBm + kb * 8192, &p.tmB, b_full, 0, kb * 64);
         tma_load_2d(sBm + kb * 8192 + 4096, &p.tmB, b_full, 0, kb * 64 + 32);
       }
+    }
+    __syncwarp();
+    {   // all 32 lanes run the loop (converged); the MMAs / commits are issued by an elected lane (umma_*_ws)
       mbar_wait(b_full, 0);
+      const uint64_t dA0 = desc_kmajor(sAr, 0), dB0 = desc_kmajor(sBm, 0);   // every other descriptor = one of these + a byte offset
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
         const int buf = n & 3, use = n >> 2;
-        if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);
+        if (use > 0) prof_wait(prof, 4, &acc_empty[buf], (use - 1) & 1, lane == 0);
         tc_fence_after();
         const uint32_t d = tmem + buf * 64;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, s = g % kDftAnaStages, it = g / kDftAnaStages;
-          mbar_wait(&full[s], it & 1);   // precise wake-up: the stage is released (empty) only after these MMAs
+          prof_wait(prof, 3, &full[s], it & 1, lane == 0);   // precise wake-up: the stage is released (empty) only after these MMAs
           tc_fence_after();
-          const uint32_t st = sAr + s * 65536;
-          const uint32_t bc = sBm + kb * 8192, bs = bc + 4096;
+          const uint64_t a0 = desc_advance(dA0, (uint32_t)s * 65536u);
+          const uint64_t bc = desc_advance(dB0, (uint32_t)kb * 8192u), bs = desc_advance(bc, 4096);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-            umma_tf32(d, desc_kmajor(st, j), desc_kmajor(bc, j), p.idesc, acc);                    // Xre  = Ye_r cos
-            umma_tf32(d, desc_kmajor(st + 49152, j), desc_kmajor(bs, j), p.idesc, 1u);            // Xre += Yo_i sin
-            umma_tf32(d + 32, desc_kmajor(st + 16384, j), desc_kmajor(bc, j), p.idesc, acc);      // Xim  = Ye_i cos
-            umma_tf32(d + 32, desc_kmajor(st + 32768, j), desc_kmajor(bs, j), p.idesc_neg, 1u);   // Xim -= Yo_r sin
+            const uint64_t bcj = desc_advance(bc, 32 * j), bsj = desc_advance(bs, 32 * j);
+            umma_tf32_ws(d, desc_advance(a0, 32 * j), bcj, p.idesc, acc);                       // Xre  = Ye_r cos
+            umma_tf32_ws(d, desc_advance(a0, 49152 + 32 * j), bsj, p.idesc, 1u);               // Xre += Yo_i sin
+            umma_tf32_ws(d + 32, desc_advance(a0, 16384 + 32 * j), bcj, p.idesc, acc);         // Xim  = Ye_i cos
+            umma_tf32_ws(d + 32, desc_advance(a0, 32768 + 32 * j), bsj, p.idesc_neg, 1u);      // Xim -= Yo_r sin
           }
-          umma_commit(&empty[s]);
+          umma_commit_ws(&empty[s]);
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit_ws(&acc_full[buf]);
       }
     }
     __syncwarp();
@@ -563,14 +649,16 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
         const int r = ti / p.ktiles, row0 = r * p.nlat + (ti - r * p.ktiles) * 16;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, rs = g % p.nraw, it = g / p.nraw;
-          if (it > 0) mbar_wait(&raw_empty[rs], (it - 1) & 1);
+          if (it > 0) prof_wait(prof, 2, &raw_empty[rs], (it - 1) & 1, true);
           mbar_expect_tx(&raw_full[rs], kRawBytes);
           const uint32_t dst = sRaw + rs * kRawBytes;
 #pragma unroll
-          for (int j1 = 0; j1 < 8; ++j1) {
-            const int sc = N2 * j1 + 32 * kb, sp = N2 * j1 + N2 - 32 * kb - 31;   // first wanted column / partner column (sp < 0 only for N2 < 31)
-            tma_load_2d(dst + j1 * kColBytes, &p.tmXc, &raw_full[rs], (sc / kAl) * kAl, row0);
-            tma_load_2d(dst + 8 * kColBytes + j1 * kParBytes, &p.tmXp, &raw_full[rs], sp < 0 ? 0 : (sp / kAl) * kAl, row0);
+          for (int gm = 0; gm < 8; ++gm) {
+            if (gm >= gs) break;
+            // one box = the columns of the row segments j1 = gm, gm + gs, ...: (kW columns) x (8 / gs segments) x (16 rows)
+            const int sc = N2 * gm + 32 * kb, sp = N2 * gm + N2 - 32 * kb - 31;   // first wanted column / partner column (sp < 0 only for N2 < 31)
+            tma_load_3d(dst + gm * (8 / gs) * kColBytes, &p.tmXc, &raw_full[rs], (sc / kAl) * kAl, 0, row0);
+            tma_load_3d(dst + 8 * kColBytes + gm * (8 / gs) * kParBytes, &p.tmXp, &raw_full[rs], sp < 0 ? 0 : (sp / kAl) * kAl, 0, row0);
           }
         }
       }
@@ -588,7 +676,11 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
       const bool kok = k < p.kp;
       const float rs = (p.mode == 0) ? ((k < p.nlat) ? __ldg(p.rowscale + k) : 0.f) : 1.f;
       const float tcomp = p.round_tf32 ? kTruncComp : 1.f;
-      mbar_wait_relaxed(&acc_full[buf], use & 1, 1000);
+      {
+        const long long tw0 = prof ? clock64() : 0;
+        mbar_wait_relaxed(&acc_full[buf], use & 1, 1000);
+        if (prof && lane == 0) atomicAdd(prof + 5, (unsigned long long)(clock64() - tw0));
+      }
       tc_fence_after();
       float vr[32], vi[32];
       const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16) + buf * 64;
@@ -631,41 +723,51 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
         const int item = pw + ii * nprod;
         const int kb = item >> 3, q = item & 7;
         const int k0 = kt16 + 2 * q;
-        const bool row0ok = k0 < p.nlat, row1ok = k0 + 1 < p.nlat;   // rows beyond nlat belong to the next image (or are out of bounds): treated as zeros
         const int g = n * nkb + kb;
         const int j2 = 32 * kb + lane;
-        const bool valid = j2 <= p.half;
-        const bool paired = valid && j2 != 0 && 2 * j2 != N2;
         const int rs = g % p.nraw;
-        mbar_wait(&raw_full[rs], (g / p.nraw) & 1);
+        prof_wait(prof, 0, &raw_full[rs], (g / p.nraw) & 1, lane == 0);
+        if (prof && lane == 0) atomicAdd(prof + 7, 1ull);
         const T* const rb = rawS + (size_t)rs * (kRawBytes / sizeof(T));
         pr xa[8], xb[8];
+        // No per-lane masks on the samples: lanes beyond N2 / 2 feed rows of E that are zero, and the column N2 / 2 (its own partner) is
+        // simply counted twice against a halved row of E; only column 0 (no partner) and rows beyond nlat are patched below, in branches
+        // that are uniform (and rarely taken).
 #pragma unroll
         for (int j1 = 0; j1 < 8; ++j1) {
-          // column box j1: [16 rows][kWc]; partner box j1: [16 rows][kWp]; both start at the wanted column rounded down to kAl
-          const int sc = N2 * j1 + 32 * kb, sp = N2 * j1 + N2 - 32 * kb - 31;
+          // column box gm: [16 rows][npb segments][kWc]; partner box: [16 rows][npb][kWp]; both start at the wanted column rounded down to kAl
+          const int gm = j1 % gs, ga = j1 / gs, npb = 8 / gs;                  // box gm, segment ga of its npb segments
+          const int sc = N2 * gm + 32 * kb, sp = N2 * gm + N2 - 32 * kb - 31;
           const int ic = sc - (sc / kAl) * kAl + lane;                          // column j2 = 32 kb + lane
-          int ip = N2 * j1 + N2 - j2 - (sp < 0 ? 0 : (sp / kAl) * kAl);          // column N2 - j2
+          int ip = N2 * gm + N2 - j2 - (sp < 0 ? 0 : (sp / kAl) * kAl);          // column N2 - j2
           ip = ip < 0 ? 0 : (ip > kWp - 1 ? kWp - 1 : ip);                      // lanes without a partner read anything inside the box
-          const T* b0 = rb + j1 * (16 * kWc) + (2 * q) * kWc;
-          const T* b1 = rb + 8 * (16 * kWc) + j1 * (16 * kWp) + (2 * q) * kWp;
-          float a0, a1, c0, c1;
+          const T* b0 = rb + gm * (16 * npb * kWc) + (2 * q) * (npb * kWc) + ga * kWc;
+          const T* b1 = rb + 8 * (16 * kWc) + gm * (16 * npb * kWp) + (2 * q) * (npb * kWp) + ga * kWp;
+          const int rowc = npb * kWc, rowp = npb * kWp;                         // row pitch inside a box
           if constexpr (kBf16) {
-            a0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[ic] << 16);
-            a1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[kWc + ic] << 16);
-            c0 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[ip] << 16);
-            c1 = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[kWp + ip] << 16);
+            xa[j1] = make_pr(__uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[ic] << 16),
+                             __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b0)[rowc + ic] << 16));
+            xb[j1] = make_pr(__uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[ip] << 16),
+                             __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(b1)[rowp + ip] << 16));
           } else {
-            a0 = reinterpret_cast<const float*>(b0)[ic];
-            a1 = reinterpret_cast<const float*>(b0)[kWc + ic];
-            c0 = reinterpret_cast<const float*>(b1)[ip];
-            c1 = reinterpret_cast<const float*>(b1)[kWp + ip];
+            xa[j1] = make_pr(reinterpret_cast<const float*>(b0)[ic], reinterpret_cast<const float*>(b0)[rowc + ic]);
+            xb[j1] = make_pr(reinterpret_cast<const float*>(b1)[ip], reinterpret_cast<const float*>(b1)[rowp + ip]);
           }
-          xa[j1] = make_pr((valid && row0ok) ? a0 : 0.f, (valid && row1ok) ? a1 : 0.f);
-          xb[j1] = make_pr((paired && row0ok) ? c0 : 0.f, (paired && row1ok) ? c1 : 0.f);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);   // samples are in registers: the raw stage may be refilled
+        if (kb == 0) {                                 // column 0 has no partner
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) xb[j1] = (lane == 0) ? make_pr(0.f, 0.f) : xb[j1];
+        }
+        if (k0 + 1 >= p.nlat) {                        // rows beyond nlat belong to the next image (or are out of bounds): zeros
+          const bool row0ok = k0 < p.nlat;
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) {
+            xa[j1] = make_pr(row0ok ? xa[j1].v.x : 0.f, 0.f);
+            xb[j1] = make_pr(row0ok ? xb[j1].v.x : 0.f, 0.f);
+          }
+        }
         pr er[8], ei[8], br[8], bi[8];
         float2 tw[8], tp[8];
         tw[0] = make_float2(1.f, 0.f);
@@ -676,7 +778,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
         dft_ana_radix8<pr>(xa, tw, er, ei);
         dft_ana_radix8<pr>(xb, tp, br, bi);
         const int s = g % kDftAnaStages, it = g / kDftAnaStages;
-        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        if (it > 0) prof_wait(prof, 1, &empty[s], (it - 1) & 1, lane == 0);
         float* const stg = reinterpret_cast<float*>(gA + (size_t)s * 65536);
         const int kr0 = 2 * q;
         // swizzled K-major position of (row c * 16 + kr, column lane): the XOR term depends on kr only (16 c is a multiple of 8)
@@ -689,9 +791,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
           else { ye_r = pr_operand(ye_r); yo_r = pr_operand(yo_r); }
           d0[c * 512] = ye_r.v.x; d1[c * 512] = ye_r.v.y;
           d0[8192 + c * 512] = yo_r.v.x; d1[8192 + c * 512] = yo_r.v.y;
-          if (c == 0) {
-            d0[4096] = 0.f; d1[4096] = 0.f; d0[12288] = 0.f; d1[12288] = 0.f;
-          } else {
+          if (c != 0) {   // the imaginary parts of class 0 are zero: those 16 rows of the two planes are cleared once at kernel start
             const pr ye_i = pr_operand(ei[c] + bi[c]), yo_i = pr_operand(ei[c] - bi[c]);
             d0[4096 + c * 512] = ye_i.v.x; d1[4096 + c * 512] = ye_i.v.y;
             d0[12288 + c * 512] = yo_i.v.x; d1[12288 + c * 512] = yo_i.v.y;
@@ -705,6 +805,9 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (kDftProfile && p.prof && threadIdx.x == 0) prof_s[6] = (unsigned long long)(clock64() - t_cta0);
+  if (kDftProfile) __syncthreads();
+  if (kDftProfile && p.prof && threadIdx.x < 16) atomicAdd(p.prof + threadIdx.x, prof_s[threadIdx.x]);
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
@@ -714,7 +817,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const int R = B * C;
   DftAnaParams p;
   memset(&p, 0, sizeof(p));
-  p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale;
+  p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.prof = dft_prof_buffer();
   p.R = R; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
   p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
@@ -730,8 +833,9 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   }
   B200_REQUIRE(bf16 || t->N2 % 4 == 0, "dft_analysis: fp32 input needs nlon %% 32 == 0 (16-byte aligned TMA boxes)");
   {
-    int rc = make_tmap_rows(&p.tmXc, x, bf16, pl->nlon, (long long)R * pl->nlat, bf16 ? 40 : 32, 16);
-    if (!rc) rc = make_tmap_rows(&p.tmXp, x, bf16, pl->nlon, (long long)R * pl->nlat, bf16 ? 40 : 36, 16);
+    p.gs = dft_box_group(t->N2, bf16 ? 2 : 4);
+    int rc = make_tmap_segments(&p.tmXc, x, bf16, pl->nlon, p.gs, (long long)R * pl->nlat, bf16 ? 40 : 32);
+    if (!rc) rc = make_tmap_segments(&p.tmXp, x, bf16, pl->nlon, p.gs, (long long)R * pl->nlat, bf16 ? 40 : 36);
     if (rc) return rc;
   }
   const size_t raw_bytes = bf16 ? (size_t)8 * 16 * (40 + 40) * 2 : (size_t)8 * 16 * (32 + 36) * 4;

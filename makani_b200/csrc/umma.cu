@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (converged); MMAs and commits are issued by an elected lane (umma_*_ws)
       int kbg = 0, i = 0;
       for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
         typename T::Tile tile;
@@ -99,9 +99,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
           mbar_wait(&full[s], it & 1);
           tc_fence_after();
           T::mma(p, tile, base + s * stage_bytes, tmem + buf * p.acc_cols, kb > 0);
-          umma_commit(&empty[s]);
+          umma_commit_ws(&empty[s]);
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit_ws(&acc_full[buf]);
         ++i;
       }
     }
@@ -153,7 +153,7 @@ struct AnaTraits {
   }
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) umma_tf32(tmem, desc_kmajor(st, j), desc_kmajor(st + 16384, j), p.idesc, (acc || j > 0) ? 1u : 0u);
+    for (int j = 0; j < 4; ++j) umma_tf32_ws(tmem, desc_advance(desc_kmajor(st, 0), 32 * j), desc_advance(desc_kmajor(st + 16384, 0), 32 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
     const int l = t.l0 + warp * 32 + lane;
@@ -219,7 +219,7 @@ struct SynTraits {
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      umma_tf32(tmem, desc_mnmajor(st, j, 4096), desc_mnmajor(st + 16384, j, 4096), p.idesc, (acc || j > 0) ? 1u : 0u);
+      umma_tf32_ws(tmem, desc_advance(desc_mnmajor(st, 0, 4096), 1024 * j), desc_advance(desc_mnmajor(st + 16384, 0, 4096), 1024 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
     const int k = t.k0 + warp * 32 + lane;
@@ -314,13 +314,13 @@ struct MixFwdTraits {
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint64_t ar = desc_kmajor(st, j), ai = desc_kmajor(st + p.offA_i, j);
-      const uint64_t br = desc_mnmajor(st + p.offB_r, j, 4096), bi = desc_mnmajor(st + p.offB_i, j, 4096);
+      const uint64_t ar = desc_advance(desc_kmajor(st, 0), 32 * j), ai = desc_advance(desc_kmajor(st + p.offA_i, 0), 32 * j);
+      const uint64_t br = desc_advance(desc_mnmajor(st + p.offB_r, 0, 4096), 1024 * j), bi = desc_advance(desc_mnmajor(st + p.offB_i, 0, 4096), 1024 * j);
       const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
-      umma_tf32(tmem, ar, br, p.idesc, a0);            // yr  = xr wr
-      umma_tf32(tmem, ai, bi, p.idesc_neg, 1u);        // yr -= xi wi
-      umma_tf32(tmem + p.N, ar, bi, p.idesc, a0);      // yi  = xr wi
-      umma_tf32(tmem + p.N, ai, br, p.idesc, 1u);      // yi += xi wr
+      umma_tf32_ws(tmem, ar, br, p.idesc, a0);            // yr  = xr wr
+      umma_tf32_ws(tmem, ai, bi, p.idesc_neg, 1u);        // yr -= xi wi
+      umma_tf32_ws(tmem + p.N, ar, bi, p.idesc, a0);      // yi  = xr wi
+      umma_tf32_ws(tmem + p.N, ai, br, p.idesc, 1u);      // yi += xi wr
     }
   }
   // rows (mi, b) -> spec rows; columns -> output channels of group g; handles cbias and the zero channel padding
@@ -388,13 +388,13 @@ struct MixDgradTraits {
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint64_t ar = desc_kmajor(st, j), ai = desc_kmajor(st + p.offA_i, j);
-      const uint64_t br = desc_kmajor(st + p.offB_r, j), bi = desc_kmajor(st + p.offB_i, j);
+      const uint64_t ar = desc_advance(desc_kmajor(st, 0), 32 * j), ai = desc_advance(desc_kmajor(st + p.offA_i, 0), 32 * j);
+      const uint64_t br = desc_advance(desc_kmajor(st + p.offB_r, 0), 32 * j), bi = desc_advance(desc_kmajor(st + p.offB_i, 0), 32 * j);
       const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
-      umma_tf32(tmem, ar, br, p.idesc, a0);            // gxr  = gr wr
-      umma_tf32(tmem, ai, bi, p.idesc, 1u);            // gxr += gi wi
-      umma_tf32(tmem + p.N, ai, br, p.idesc, a0);      // gxi  = gi wr
-      umma_tf32(tmem + p.N, ar, bi, p.idesc_neg, 1u);  // gxi -= gr wi
+      umma_tf32_ws(tmem, ar, br, p.idesc, a0);            // gxr  = gr wr
+      umma_tf32_ws(tmem, ai, bi, p.idesc, 1u);            // gxr += gi wi
+      umma_tf32_ws(tmem + p.N, ai, br, p.idesc, a0);      // gxi  = gi wr
+      umma_tf32_ws(tmem + p.N, ar, bi, p.idesc_neg, 1u);  // gxi -= gr wi
     }
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
@@ -441,13 +441,13 @@ struct MixWgradTraits {
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint64_t ar = desc_mnmajor(st, j, 4096), ai = desc_mnmajor(st + p.offA_i, j, 4096);
-      const uint64_t br = desc_mnmajor(st + p.offB_r, j, 4096), bi = desc_mnmajor(st + p.offB_i, j, 4096);
+      const uint64_t ar = desc_advance(desc_mnmajor(st, 0, 4096), 1024 * j), ai = desc_advance(desc_mnmajor(st + p.offA_i, 0, 4096), 1024 * j);
+      const uint64_t br = desc_advance(desc_mnmajor(st + p.offB_r, 0, 4096), 1024 * j), bi = desc_advance(desc_mnmajor(st + p.offB_i, 0, 4096), 1024 * j);
       const uint32_t a0 = (acc || j > 0) ? 1u : 0u;
-      umma_tf32(tmem, ar, br, p.idesc, a0);            // gwr  = xr gr
-      umma_tf32(tmem, ai, bi, p.idesc, 1u);            // gwr += xi gi
-      umma_tf32(tmem + p.N, ar, bi, p.idesc, a0);      // gwi  = xr gi
-      umma_tf32(tmem + p.N, ai, br, p.idesc_neg, 1u);  // gwi -= xi gr
+      umma_tf32_ws(tmem, ar, br, p.idesc, a0);            // gwr  = xr gr
+      umma_tf32_ws(tmem, ai, bi, p.idesc, 1u);            // gwr += xi gi
+      umma_tf32_ws(tmem + p.N, ar, bi, p.idesc, a0);      // gwi  = xr gi
+      umma_tf32_ws(tmem + p.N, ai, br, p.idesc_neg, 1u);  // gwi -= xi gr
     }
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
