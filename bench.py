@@ -354,8 +354,19 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dp_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # the gradient all-reduce runs beside two persistent kernels that leave it B200SHT_OVERLAP_SMS (8) SMs: a communicator of its own,
+        # capped at as many CTAs, so that it starts at once instead of waiting for a kernel boundary
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(os.environ.get("B200SHT_OVERLAP_SMS", "8")) or 8
+            opts.config.min_ctas = 1
+            dp_group = dist.new_group(list(range(world)), pg_options=opts)
+        except Exception as e:   # older torch / NCCL: default communicator
+            sys.stderr.write(f"bench: NCCL communicator with max_ctas unavailable ({e}); using the default one\n")
+            dp_group = None
     wl = args.workload
     nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, L, M, C = WORKLOADS[wl]
     act_dtype = torch.bfloat16 if args.act == "bf16" else torch.float32
@@ -492,7 +503,7 @@ def run_gpu_arm(args):
         if world > 1:
             side.wait_event(conv.wgrad_ready_event)
             with torch.cuda.stream(side):
-                dist.all_reduce(torch.view_as_real(conv.weight.grad))
+                dist.all_reduce(torch.view_as_real(conv.weight.grad), group=dp_group)
             conv.weight.grad.record_stream(side)
             torch.cuda.current_stream(dev).wait_stream(side)
 
@@ -662,7 +673,7 @@ def run_gpu_arm(args):
         "metric": "SFNO-block fwd+bwd samples/sec", "value": world * 1e3 / ms_dev, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if precision == "tf32" else "f32",
         "data": "synthetic",
-        "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": "tcgen05 kind::tf32, fp32 accumulate" if precision == "tf32" else "fp32 FMA (CUDA cores)",
+        "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": {"tf32": "tcgen05 kind::tf32, fp32 accumulate", "fp32x3": "Legendre: 3 x TF32 on tcgen05 (fp32 operands); mix, FFT: fp32 FMA"}.get(precision, "fp32 FMA (CUDA cores)"),
                    "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "operator": "dhconv", "lmax": L, "mmax": M,
                    "l2": f"256 MiB buffer written between timed iterations (L2 flush); input {x_host.numel() * x_host.element_size() / 1e6:.0f} MB",
                    "weight_relayout_in_step": True, "flops_fwd_bwd_nnz": flops_fwd_bwd(wl)},
@@ -852,7 +863,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sfno_block_721x1440x73", choices=sorted(WORKLOADS) + sorted(MODEL_WORKLOADS))
-    ap.add_argument("--precision", default="best", choices=["best", "fp32", "tf32"])
+    ap.add_argument("--precision", default="best", choices=["best", "fp32", "tf32", "fp32x3"])
     ap.add_argument("--act", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stages", action="store_true", help="skip per-stage kernel timing")

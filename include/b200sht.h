@@ -52,7 +52,12 @@ typedef enum { B200SHT_F32 = 0, B200SHT_BF16 = 1 } b200sht_dtype;
 /* arithmetic of the Legendre / channel-mix contractions */
 typedef enum {
   B200SHT_PREC_FP32 = 0, /* fp32 FMA on CUDA cores (reference tests run with TF32 disabled)          */
-  B200SHT_PREC_TF32 = 1  /* tcgen05 kind::tf32, fp32 accumulate in TMEM (reference training: allow_tf32) */
+  B200SHT_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (reference training: allow_tf32) */
+  B200SHT_PREC_FP32X3 = 2 /* fp32 operands on the tensor cores: Legendre stages as 3 x TF32 (hi.hi + hi.lo + lo.hi into one TMEM accumulator),
+                             longitude transform and channel mix as in FP32.  Element errors stay inside rtol 1e-5 (atol = rtol max|ref|), relative
+                             L2 ~ 1e-6 .. 8e-6 growing with nlat (the tensor core truncates its fp32 accumulator on every add; the CUDA-core FP32 mode
+                             rounds to nearest and stays at ~ 3e-7): ~1.7 x the speed of FP32 at 721 x 1440.  Uses a per-device scratch buffer for the
+                             operand residuals: issue calls of this mode from one stream per device.                                          */
 } b200sht_precision;
 
 typedef enum {

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("B200SHT_LIBRARY") or os.path.join(_HERE, "libb200sht.
 HEADER_PATH = os.path.join(_HERE, "..", "include", "b200sht.h")
 
 F32, BF16 = 0, 1
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_FP32X3 = 0, 1, 2
 OP_DHCONV, OP_DIAGONAL, OP_SEP_DHCONV, OP_SEP_DIAGONAL, OP_SHARED, OP_LDEP = range(6)
 DENSE_FLAG = 0x100
 

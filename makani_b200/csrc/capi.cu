@@ -7,6 +7,7 @@
 #include <vector>
 
 namespace b200sht {
+int& sm_reserve() { static thread_local int r = 0; return r; }
 
 static thread_local std::string g_last_error;
 
@@ -43,8 +44,10 @@ int dft_plan_init(Plan* pl);
 void dft_plan_destroy(Plan* pl);
 int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out);
 int dft_profile_read(unsigned long long* out16);
-int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st);
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st);
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo = nullptr);
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo = nullptr);
+int umma_plan_table_lo(const Plan* pl);
+int tf32_residual(const float* src, float* dst, size_t n, cudaStream_t st);
 bool dft_usable(const Plan* pl);
 int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co, cudaStream_t st);
 int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
@@ -185,11 +188,32 @@ int b200sht_fft_synthesis(const b200sht_plan* pl, const float* latspec, void* y,
   return fft_synthesis(pl, latspec, y, dtype, B, C, bias, scale_mode, S(stream));
 }
 
+// ---------------------------------------------------------------------------------- fp32 operands on the tensor cores
+// B200SHT_PREC_FP32X3: the Legendre stages run as 3 x TF32 (hi.hi + hi.lo + lo.hi with fp32 accumulation in TMEM) instead of the CUDA-core
+// kernels.  The residual of the activation operand lives in a per-device scratch buffer that grows on demand: calls of this mode on one
+// device must be issued from one stream at a time (they are stream-ordered through the same buffer).
+static float* residual_scratch(size_t bytes) {
+  struct Pool { float* p = nullptr; size_t n = 0; };
+  static std::mutex mu;
+  static Pool pools[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Pool& pool = pools[dev];
+  if (pool.n < bytes) {
+    if (pool.p) cudaFree(pool.p);   // synchronises the device: no kernel still reads the old buffer
+    pool.p = nullptr; pool.n = 0;
+    if (cudaMalloc(&pool.p, bytes) != cudaSuccess) { pool.p = nullptr; return nullptr; }
+    pool.n = bytes;
+  }
+  return pool.p;
+}
+
 static int check_precision(int umma_ok, int precision, const char* who) {
   if (precision == B200SHT_PREC_FP32) return 0;
-  if (precision == B200SHT_PREC_TF32) {
+  if (precision == B200SHT_PREC_TF32 || precision == B200SHT_PREC_FP32X3) {
     if (!umma_ok) {
-      set_error("%s: the tcgen05 (TF32) path is not available on this device/build; refusing to fall back silently", who);
+      set_error("%s: the tcgen05 (TF32 / 3 x TF32) path is not available on this device/build; refusing to fall back silently", who);
       return B200SHT_ERR_UNSUPPORTED;
     }
     return 0;
@@ -203,8 +227,17 @@ int b200sht_legendre_analysis(const b200sht_plan* pl, const float* latspec, floa
   B200_REQUIRE(!pl->no_table, "legendre_analysis: FFT-only plan");
   int rc = check_precision(pl->umma_ok, precision, "legendre_analysis");
   if (rc) return rc;
-  return precision == B200SHT_PREC_TF32 ? legendre_analysis_umma(pl, latspec, spec, B, C, S(stream))
-                                        : legendre_analysis_simt(pl, latspec, spec, B, C, S(stream));
+  if (precision == B200SHT_PREC_TF32) return legendre_analysis_umma(pl, latspec, spec, B, C, S(stream));
+  if (precision == B200SHT_PREC_FP32X3) {
+    const size_t n = (size_t)pl->mmax * 2 * B * C * pl->kp;
+    float* lo = residual_scratch(n * sizeof(float));
+    B200_REQUIRE(lo != nullptr, "legendre_analysis (3 x TF32): cannot allocate %zu bytes of scratch", n * sizeof(float));
+    rc = umma_plan_table_lo(pl);
+    if (!rc) rc = tf32_residual(latspec, lo, n, S(stream));
+    if (!rc) rc = legendre_analysis_umma(pl, latspec, spec, B, C, S(stream), lo);
+    return rc;
+  }
+  return legendre_analysis_simt(pl, latspec, spec, B, C, S(stream));
 }
 
 int b200sht_legendre_synthesis(const b200sht_plan* pl, const float* spec, float* latspec, int B, int C, int precision, void* stream) {
@@ -212,8 +245,17 @@ int b200sht_legendre_synthesis(const b200sht_plan* pl, const float* spec, float*
   B200_REQUIRE(!pl->no_table, "legendre_synthesis: FFT-only plan");
   int rc = check_precision(pl->umma_ok, precision, "legendre_synthesis");
   if (rc) return rc;
-  return precision == B200SHT_PREC_TF32 ? legendre_synthesis_umma(pl, spec, latspec, B, C, 0, S(stream))
-                                        : legendre_synthesis_simt(pl, spec, latspec, B, C, S(stream));
+  if (precision == B200SHT_PREC_TF32) return legendre_synthesis_umma(pl, spec, latspec, B, C, 0, S(stream));
+  if (precision == B200SHT_PREC_FP32X3) {
+    const size_t n = (size_t)b200sht_spec_elems(pl, B, C);
+    float* lo = residual_scratch(n * sizeof(float));
+    B200_REQUIRE(lo != nullptr, "legendre_synthesis (3 x TF32): cannot allocate %zu bytes of scratch", n * sizeof(float));
+    rc = umma_plan_table_lo(pl);
+    if (!rc) rc = tf32_residual(spec, lo, n, S(stream));
+    if (!rc) rc = legendre_synthesis_umma(pl, spec, latspec, B, C, 0, S(stream), lo);
+    return rc;
+  }
+  return legendre_synthesis_simt(pl, spec, latspec, B, C, S(stream));
 }
 
 int b200sht_legendre_synthesis_tiled(const b200sht_plan* pl, const float* spec, float* latspec, int B, int C, void* stream) {
@@ -467,8 +509,10 @@ int b200sht_spectral_conv_backward_ex(const b200sht_plan* f, const b200sht_plan*
   rc = b200sht_fft_analysis(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
   if (!rc && gbias) rc = b200sht_bias_grad(v, ws.lat_out, gbias, d->B, d->Cout, stream);
   if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cout, d->precision, stream);
-  if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, gx ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G, d->Cin, d->Cout,
-                                     d->precision, stream);
+  // with an event to signal, the weight gradient goes first and the input gradient of the mix joins the overlapped stages below
+  const bool split_mix = wgrad_ready_event != nullptr && gw != nullptr && gx != nullptr;
+  if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, (gx && !split_mix) ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G,
+                                     d->Cin, d->Cout, d->precision, stream);
   // the weight gradient is final here: hand it to the caller (native layout + event) BEFORE the two input-gradient stages, so that a
   // data-parallel all-reduce on another stream overlaps legendre_synthesis + fft_synthesis instead of trailing the whole backward pass
   if (!rc && gw && gw_native) {
@@ -477,6 +521,17 @@ int b200sht_spectral_conv_backward_ex(const b200sht_plan* f, const b200sht_plan*
     rc = b200sht_mix_weight_unpack(d->op, static_cast<const float*>(gw), gw_native, f->lmax, d->G, d->Cin, d->Cout, stream);
   }
   if (!rc && wgrad_ready_event) B200_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(wgrad_ready_event), S(stream)));
+  // the caller overlaps a collective with what follows: leave it a few SMs (B200SHT_OVERLAP_SMS, default 8; 0 = none)
+  struct ReserveGuard {
+    int saved;
+    explicit ReserveGuard(bool on) : saved(sm_reserve()) {
+      static const int n = [] { const char* e = getenv("B200SHT_OVERLAP_SMS"); return e ? atoi(e) : 8; }();
+      if (on) sm_reserve() = n;
+    }
+    ~ReserveGuard() { sm_reserve() = saved; }
+  } reserve_guard(wgrad_ready_event != nullptr);
+  if (!rc && split_mix)
+    rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, ws.spec_in, nullptr, nullptr, d->B, d->G, d->Cin, d->Cout, d->precision, stream);
   if (!rc && gx) {
     if (gresidual) {
       rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);

@@ -67,6 +67,7 @@ struct Plan {
   int dense;            // dims-only plans: packed spec tensors store every (l, m) entry (no block triangle)
   float* d_table;       // [mmax][lmax][kp]
   float* d_table_tf32;  // same, rounded to nearest TF32 (operand of the tcgen05 kernels); null when that path is unavailable
+  float* d_table_lo;    // d_table - d_table_tf32 (second term of the 3 x TF32 strict-fp32 mode); allocated at its first use
   float* d_rowscale;    // [kp]  quad_w[k] * 2 pi / nlon (0 in the padding)
   float2* d_twiddle;    // [nlon] exp(-2 pi i t / nlon)
   FftPlan fft;
@@ -75,6 +76,13 @@ struct Plan {
   void* umma_state;     // TMA descriptors etc. (owned by umma translation unit)
   void* dft_state;      // tensor-core DFT tables (dft.cu); null when the grid is outside its range or tcgen05 is unavailable
 };
+
+// SMs left free by the persistent kernels launched from this thread (0 = use them all).  Set around the stages that are meant to run beside
+// a collective on another stream (b200sht_spectral_conv_backward_ex): a persistent one-CTA-per-SM kernel leaves an NCCL kernel nowhere to
+// run, the collective then lands between two kernels and the next one starts on fewer SMs with a static tile assignment -- slower than
+// giving the SMs away up front.
+int& sm_reserve();
+inline int usable_sms(int sms) { const int r = sm_reserve(); return (r > 0 && sms - r >= 1) ? sms - r : sms; }
 
 }  // namespace b200sht
 

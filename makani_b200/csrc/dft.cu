@@ -467,7 +467,7 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
     if (rc) return rc;
   }
   const size_t smem = 1024 + 32768 + (size_t)kDftSynStages * 16384 + ((8 * (size_t)t->N2 * 8 + 15) & ~(size_t)15) + (2 * kDftSynStages + 5) * 8 + 16;
-  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  const int sms = usable_sms(pl->sm_count > 0 ? pl->sm_count : 148);
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
 #define B200_LAUNCH_SYN(TT, NN)                                                                                                          \
   do {                                                                                                                                  \
@@ -840,7 +840,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   }
   const size_t raw_bytes = bf16 ? (size_t)8 * 16 * (40 + 40) * 2 : (size_t)8 * 16 * (32 + 36) * 4;
   const size_t smem = 1024 + 3 * 8192 + (size_t)kDftAnaStages * 65536 + p.nraw * raw_bytes + 3 * 7 * 32 * 8 + 256;
-  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  const int sms = usable_sms(pl->sm_count > 0 ? pl->sm_count : 148);
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
   const int threads = 32 * (6 + (t->nkb == 3 ? 12 : 8));
 #define B200_LAUNCH_ANA(TT, NN)                                                                                                          \

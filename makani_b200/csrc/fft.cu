@@ -761,7 +761,7 @@ static int launch_ct(const Plan* pl, int dir, const void* in, void* out, const F
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
-  const int sms = pl->sm_count > 0 ? pl->sm_count : 148;
+  const int sms = usable_sms(pl->sm_count > 0 ? pl->sm_count : 148);
   dim3 grid(ntiles < per_sm * sms ? ntiles : per_sm * sms);
   if (dir == 0) {
     auto k = fft_analysis_ct_kernel<T, ROWS, GROUPS, TPG, R0, R1, R2, MINB>;

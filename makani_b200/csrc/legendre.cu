@@ -43,6 +43,37 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
   if (i < n) dst[i] = tf32_rn(src[i]);
 }
 
+// 3 x TF32: an fp32 operand v enters a kind::tf32 MMA as trunc(v) (the tensor core ignores the 13 low mantissa bits); the residual
+// v - trunc(v) is exact in fp32 and is fed to a second MMA, rounded to nearest TF32 here (its own truncation would add a 2^-21 bias).
+__global__ void tf32_residual_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = src[i];
+  float4 r;
+  r.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+  r.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+  r.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+  r.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+  dst[i] = r;
+}
+// n floats, n % 4 == 0, both pointers 16-byte aligned
+int tf32_residual(const float* src, float* dst, size_t n, cudaStream_t st) {
+  const size_t n4 = n / 4;
+  if (n4 == 0) return 0;
+  tf32_residual_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+__global__ void table_lo_kernel(const float* __restrict__ full, const float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lo[i] = tf32_rn(full[i] - hi[i]);
+}
+int table_residual(const float* full, const float* hi, float* lo, size_t n, cudaStream_t st) {
+  table_lo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(full, hi, lo, n);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
 int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st) {
   round_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
   B200_CHECK_LAUNCH();

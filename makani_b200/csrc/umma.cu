@@ -17,6 +17,7 @@
 //
 // All shared-memory operand tiles use the 128-byte swizzle; every TMA box is [rows][32 floats] so it lands as rows of 128 B.
 #include "umma_common.cuh"
+#include <mutex>
 
 namespace b200sht {
 
@@ -30,6 +31,8 @@ struct EngineParams {
   uint32_t stage_bytes, tx_bytes, tmem_cols;
   int gx, gy, gz;          // logical tile grid (x fastest); CTAs walk it round-robin
   int acc_cols, nbuf;      // TMEM columns of one accumulator set, number of sets (2: epilogue of tile i overlaps main loop of i+1)
+  int split;               // 3 x TF32 (strict fp32 on the tensor cores): every stage also holds the residual tiles of both operands, `lo_off`
+  uint32_t lo_off;         // bytes after the main tiles, and each MMA becomes hi.hi + hi.lo + lo.hi into the same accumulator
 };
 
 
@@ -133,6 +136,7 @@ struct AnaTraits {
   struct Params : EngineParams {
     alignas(64) CUtensorMap tmA;  // table  (k, l, m)       box (32, 128, 1)
     alignas(64) CUtensorMap tmB;  // X      (k, c, pb, m)   box (32, Cc, PBc, 1)
+    alignas(64) CUtensorMap tmA_lo, tmB_lo;   // residuals of the table and of X (split mode)
     float* spec;
     int L, M, nlat, C, cp, PB, Cc, PBc, n_ct, N, m0;
     uint32_t idesc;
@@ -150,10 +154,22 @@ struct AnaTraits {
   __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
     tma_load_3d(st, &p.tmA, bar, kb * 32, t.l0, t.m);
     tma_load_4d(st + 16384, &p.tmB, bar, kb * 32, t.c0, t.pb0, t.m);
+    if (p.split) {
+      tma_load_3d(st + p.lo_off, &p.tmA_lo, bar, kb * 32, t.l0, t.m);
+      tma_load_4d(st + p.lo_off + 16384, &p.tmB_lo, bar, kb * 32, t.c0, t.pb0, t.m);
+    }
   }
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+    const uint64_t a = desc_kmajor(st, 0), b = desc_kmajor(st + 16384, 0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) umma_tf32_ws(tmem, desc_advance(desc_kmajor(st, 0), 32 * j), desc_advance(desc_kmajor(st + 16384, 0), 32 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
+    for (int j = 0; j < 4; ++j) umma_tf32_ws(tmem, desc_advance(a, 32 * j), desc_advance(b, 32 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
+    if (p.split) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        umma_tf32_ws(tmem, desc_advance(a, 32 * j), desc_advance(b, p.lo_off + 32 * j), p.idesc, 1u);   // hi . lo
+        umma_tf32_ws(tmem, desc_advance(a, p.lo_off + 32 * j), desc_advance(b, 32 * j), p.idesc, 1u);   // lo . hi
+      }
+    }
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
     const int l = t.l0 + warp * 32 + lane;
@@ -170,8 +186,12 @@ struct AnaTraits {
         if (n >= ncols) break;
         const int pbi = n / p.Cc, ci = n - pbi * p.Cc;
         const int pb = t.pb0 + pbi, c = t.c0 + ci;
-        if (pb < p.PB && c < p.cp)  // consumers are kind::tf32 MMAs: round to nearest here
-          *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(tf32_rn(v[q * 4]), tf32_rn(v[q * 4 + 1]), tf32_rn(v[q * 4 + 2]), tf32_rn(v[q * 4 + 3]));
+        if (pb < p.PB && c < p.cp) {
+          if (p.split)   // strict fp32: the coefficients stay as accumulated
+            *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          else           // consumers are kind::tf32 MMAs: round to nearest here
+            *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(tf32_rn(v[q * 4]), tf32_rn(v[q * 4 + 1]), tf32_rn(v[q * 4 + 2]), tf32_rn(v[q * 4 + 3]));
+        }
       }
     }
   }
@@ -194,6 +214,7 @@ struct SynTraits {
   struct Params : EngineParams {
     alignas(64) CUtensorMap tmA;  // table (k, l, m)   box (32, 32, 1)   MN-major A (M = k)
     alignas(64) CUtensorMap tmB;  // spec  (n, m, l)   box (32, 1, 32)   MN-major B (N = n)
+    alignas(64) CUtensorMap tmA_lo, tmB_lo;   // residuals of the table and of spec (split mode)
     float* Z;
     int L, M, nlat, kp, C, cp, PB, nblk, N, m0;
     int tiled, M2, KT, B;   // tiled output for the tensor-core DFT (dft.cu): Z[r][k / 8][p][m / 8][m % 8][k % 8], orders padded to 8 * M2
@@ -215,11 +236,23 @@ struct SynTraits {
 #pragma unroll
     for (int b = 0; b < 4; ++b) tma_load_3d(st + b * 4096, &p.tmA, bar, t.k0 + 32 * b, l, t.m);
     for (int b = 0; b < p.nblk; ++b) tma_load_3d(st + 16384 + b * 4096, &p.tmB, bar, t.n0 + 32 * b, t.m, l);
+    if (p.split) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) tma_load_3d(st + p.lo_off + b * 4096, &p.tmA_lo, bar, t.k0 + 32 * b, l, t.m);
+      for (int b = 0; b < p.nblk; ++b) tma_load_3d(st + p.lo_off + 16384 + b * 4096, &p.tmB_lo, bar, t.n0 + 32 * b, t.m, l);
+    }
   }
   __device__ static void mma(const Params& p, const Tile&, uint32_t st, uint32_t tmem, bool acc) {
+    const uint64_t a = desc_mnmajor(st, 0, 4096), b = desc_mnmajor(st + 16384, 0, 4096);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      umma_tf32_ws(tmem, desc_advance(desc_mnmajor(st, 0, 4096), 1024 * j), desc_advance(desc_mnmajor(st + 16384, 0, 4096), 1024 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
+    for (int j = 0; j < 4; ++j) umma_tf32_ws(tmem, desc_advance(a, 1024 * j), desc_advance(b, 1024 * j), p.idesc, (acc || j > 0) ? 1u : 0u);
+    if (p.split) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        umma_tf32_ws(tmem, desc_advance(a, 1024 * j), desc_advance(b, p.lo_off + 1024 * j), p.idesc, 1u);   // hi . lo
+        umma_tf32_ws(tmem, desc_advance(a, p.lo_off + 1024 * j), desc_advance(b, 1024 * j), p.idesc, 1u);   // lo . hi
+      }
+    }
   }
   __device__ static void epilogue(const Params& p, const Tile& t, uint32_t tmem, int warp, int lane, int nk, int* scratch) {
     const int k = t.k0 + warp * 32 + lane;
@@ -492,6 +525,7 @@ int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st);  
 int umma_plan_init(Plan* pl) {
   pl->umma_state = nullptr;
   pl->d_table_tf32 = nullptr;
+  pl->d_table_lo = nullptr;
   if (!umma_available()) return -1;
   const size_t n = (size_t)pl->mmax * pl->lmax * pl->kp;
   if (cudaMalloc(&pl->d_table_tf32, n * sizeof(float)) != cudaSuccess) { pl->d_table_tf32 = nullptr; return -1; }
@@ -505,6 +539,26 @@ int umma_plan_init(Plan* pl) {
 void umma_plan_destroy(Plan* pl) {
   if (pl->d_table_tf32) cudaFree(pl->d_table_tf32);
   pl->d_table_tf32 = nullptr;
+  if (pl->d_table_lo) cudaFree(pl->d_table_lo);
+  pl->d_table_lo = nullptr;
+}
+
+int table_residual(const float* full, const float* hi, float* lo, size_t n, cudaStream_t st);  // legendre.cu
+// residual table of the 3 x TF32 mode: built the first time a strict-fp32 Legendre stage runs on the tensor cores (most plans never need it)
+int umma_plan_table_lo(const Plan* cpl) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Plan* pl = const_cast<Plan*>(cpl);
+  if (pl->d_table_lo) return 0;
+  B200_REQUIRE(pl->d_table && pl->d_table_tf32, "3 x TF32: the plan has no Legendre table");
+  const size_t n = (size_t)pl->mmax * pl->lmax * pl->kp;
+  float* lo = nullptr;
+  B200_CHECK_CUDA(cudaMalloc(&lo, n * sizeof(float)));
+  int rc = table_residual(pl->d_table, pl->d_table_tf32, lo, n, 0);
+  if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = B200SHT_ERR_CUDA;
+  if (rc) { cudaFree(lo); return rc; }
+  pl->d_table_lo = lo;
+  return 0;
 }
 
 constexpr size_t kSmemMax = 232448 - 4096;  // 227 KB minus barriers / epilogue scratch / alignment slack
@@ -544,7 +598,8 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
   B200_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // static round-robin over tiles: an odd CTA count not divisible by 3 keeps tile-grid periods (2 l- or m-tiles, 3 or 6 n/k-tiles)
   // from locking heavy tiles onto the same CTAs
-  int ctas = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  const int sms = usable_sms(sm_count());
+  int ctas = (int)(ntiles < sms ? ntiles : sms);
   while (ctas > 1 && (ctas % 2 == 0 || ctas % 3 == 0)) --ctas;
   umma_kernel<T><<<ctas, kUmmaThreads, smem, st>>>(p);
   B200_CHECK_LAUNCH();
@@ -552,7 +607,7 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- Legendre
-int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st) {
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo) {
   AnaTraits::Params p;
   memset(&p, 0, sizeof(p));
   const int cp = round_up(C, 4), PB = 2 * B;
@@ -575,14 +630,26 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
     if (rc) return rc;
   }
   const uint32_t bbytes = (uint32_t)round_up(p.N * 128, 1024);
-  pick_stages(&p, 16384 + bbytes, ceil_div(pl->nlat, 32));
-  p.tx_bytes = 16384 + (uint32_t)rows * 128;
+  p.split = X_lo != nullptr;
+  if (p.split) {
+    B200_REQUIRE(pl->d_table_lo != nullptr, "legendre_analysis (3 x TF32): the residual table is missing");
+    long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
+    int bx[3] = {32, 128, 1};
+    int rc = make_tmap(&p.tmA_lo, pl->d_table_lo, 3, d, s, bx);
+    long long d4[4] = {pl->nlat, C, PB, pl->mmax}, s4[4] = {1, pl->kp, (long long)C * pl->kp, (long long)PB * C * pl->kp};
+    int bx4[4] = {32, p.Cc, p.PBc, 1};
+    if (!rc) rc = make_tmap(&p.tmB_lo, X_lo, 4, d4, s4, bx4);
+    if (rc) return rc;
+    p.lo_off = 16384 + bbytes;
+  }
+  pick_stages(&p, (16384 + bbytes) * (p.split ? 2 : 1), ceil_div(pl->nlat, 32));
+  p.tx_bytes = (16384 + (uint32_t)rows * 128) * (p.split ? 2 : 1);
   set_accumulators(&p, p.N);
   dim3 grid(ceil_div(pl->lmax, 128), p.n_ct * ceil_div(PB, p.PBc), pl->mmax);
   return launch<AnaTraits>(p, grid, st);
 }
 
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st) {
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo) {
   SynTraits::Params p;
   memset(&p, 0, sizeof(p));
   const int cp = round_up(C, 4), PB = 2 * B, JP = PB * cp;
@@ -604,8 +671,20 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
     int rc = make_tmap(&p.tmB, spec, 3, d, s, bx, true);
     if (rc) return rc;
   }
-  pick_stages(&p, 16384 + 4096 * p.nblk, ceil_div(pl->lmax, 32));
-  p.tx_bytes = 16384 + 4096 * p.nblk;
+  p.split = spec_lo != nullptr;
+  if (p.split) {
+    B200_REQUIRE(pl->d_table_lo != nullptr, "legendre_synthesis (3 x TF32): the residual table is missing");
+    long long d[3] = {pl->nlat, pl->lmax, pl->mmax}, s[3] = {1, pl->kp, (long long)pl->lmax * pl->kp};
+    int bx[3] = {32, 32, 1};
+    int rc = make_tmap(&p.tmA_lo, pl->d_table_lo, 3, d, s, bx, true);
+    long long d2[3] = {JP, pl->mmax, pl->lmax}, s2[3] = {1, JP, (long long)pl->mmax * JP};
+    int bx2[3] = {32, 1, 32};
+    if (!rc) rc = make_tmap(&p.tmB_lo, spec_lo, 3, d2, s2, bx2, true);
+    if (rc) return rc;
+    p.lo_off = 16384 + 4096 * p.nblk;
+  }
+  pick_stages(&p, (16384 + 4096 * p.nblk) * (p.split ? 2 : 1), ceil_div(pl->lmax, 32));
+  p.tx_bytes = (16384 + 4096 * p.nblk) * (p.split ? 2 : 1);
   set_accumulators(&p, p.N);
   dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), tiled ? 8 * p.M2 : pl->mmax);
   return launch<SynTraits>(p, grid, st);

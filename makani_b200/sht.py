@@ -40,14 +40,18 @@ def _dtype_code(dt):
 
 
 def resolve_precision(precision="auto"):
-    """'fp32' -> CUDA-core fp32 FMA; 'tf32' -> tcgen05 TF32; 'auto' follows torch.backends.cuda.matmul.allow_tf32, which is
-    how the reference picks its arithmetic (train.py:87 sets allow_tf32=True, tests/testutils.py:55-66 disable it)."""
+    """'fp32' -> CUDA-core fp32 FMA; 'tf32' -> tcgen05 TF32; 'fp32x3' -> fp32 operands with the Legendre stages as 3 x TF32 on the
+    tensor cores (rtol 1e-5 element bound, ~1.7 x faster than 'fp32'; see B200SHT_PREC_FP32X3 in include/b200sht.h); 'auto' follows
+    torch.backends.cuda.matmul.allow_tf32, which is how the reference picks its arithmetic (train.py:87 sets allow_tf32=True,
+    tests/testutils.py:55-66 disable it)."""
     if precision == "auto":
         precision = "tf32" if torch.backends.cuda.matmul.allow_tf32 else "fp32"
     if precision == "fp32":
         return _lib.PREC_FP32
     if precision == "tf32":
         return _lib.PREC_TF32
+    if precision == "fp32x3":
+        return _lib.PREC_FP32X3
     raise ValueError(f"unknown precision {precision!r}")
 
 
