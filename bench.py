@@ -516,6 +516,10 @@ def run_gpu_arm(args):
                         "b200sht_spectral_conv_forward": 5, "b200sht_spectral_conv_backward": 6,
                         "b200sht_spectral_conv_backward_ex": 7,   # + the weight-gradient re-layout, now inside the call
                         "b200sht_legendre_synthesis_tiled": 1}
+    if precision == "fp32x3":   # + one operand-residual kernel per Legendre stage
+        for k, extra in (("b200sht_legendre_analysis", 1), ("b200sht_legendre_synthesis", 1), ("b200sht_spectral_conv_forward", 2),
+                         ("b200sht_spectral_conv_backward", 2), ("b200sht_spectral_conv_backward_ex", 2)):
+            kernels_per_call[k] += extra
     orig_call = _lib.call
 
     def counting_call(name, *a):
@@ -671,7 +675,7 @@ def run_gpu_arm(args):
     x_bytes = x_host.numel() * x_host.element_size()
     line = {
         "metric": "SFNO-block fwd+bwd samples/sec", "value": world * 1e3 / ms_dev, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if precision == "tf32" else "f32",
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if precision == "tf32" else ("f32 (3 x tf32 Legendre)" if precision == "fp32x3" else "f32"),
         "data": "synthetic",
         "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": {"tf32": "tcgen05 kind::tf32, fp32 accumulate", "fp32x3": "Legendre: 3 x TF32 on tcgen05 (fp32 operands); mix, FFT: fp32 FMA"}.get(precision, "fp32 FMA (CUDA cores)"),
                    "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "operator": "dhconv", "lmax": L, "mmax": M,

@@ -6,6 +6,7 @@ The product path has no CPU or PyTorch fallback: if the library cannot be loaded
 import ctypes
 import os
 import re
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200SHT_LIBRARY: another build of the same library (e.g. the wait-profile build of scripts/dft_waitprof.py); default: the in-tree one
@@ -118,7 +119,30 @@ def check(rc, what=""):
         raise B200ShtError(f"{what} failed (status {rc}): {msg}")
 
 
+_tls = threading.local()
+
+
+def launch_stream(device):
+    """The stream argument of a library call: torch's current stream of `device`.  Also remembers the device for `call`, which makes it
+    current around the launch when it is not (a tensor on cuda:1 while cuda:0 is current would otherwise launch into the wrong context)."""
+    import torch
+
+    dev = torch.device(device)
+    _tls.device = dev.index if dev.index is not None else torch.cuda.current_device()
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
 def call(name, *args):
     lib = load()
+    dev = getattr(_tls, "device", None)
+    _tls.device = None
+    if dev is not None:
+        import torch
+
+        if dev != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                rc = getattr(lib, name)(*args)
+            check(rc, name)
+            return
     rc = getattr(lib, name)(*args)
     check(rc, name)

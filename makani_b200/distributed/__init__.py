@@ -144,7 +144,7 @@ def _p(t):
 
 
 def _st(dev):
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    return L.launch_stream(dev)
 
 
 def _dt(dtype):

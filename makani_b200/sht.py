@@ -28,7 +28,7 @@ def _ptr(t):
 
 
 def _stream(device):
-    return _VP(torch.cuda.current_stream(device).cuda_stream)
+    return _lib.launch_stream(device)
 
 
 def _dtype_code(dt):

@@ -11,6 +11,8 @@ The whole forward is 5 kernels: longitude FFT -> Legendre analysis -> channel mi
 import ctypes
 import math
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -38,17 +40,32 @@ class PackedWeightCache:
     def __init__(self):
         self.enabled = True
         self._key = None
+        self._ref = None      # weak reference to the parameter the packed copy was made from
         self._packed = None
 
+    def invalidate(self):
+        """Forget the packed copy.  Needed after writes that do not bump the version counter (`weight.data.copy_()`, kernels writing through
+        `data_ptr()`); `SpectralConv` / `SpectralAttention` call it from `_apply` and `load_state_dict`."""
+        self._key = self._ref = self._packed = None
+
     def get(self, w, op, L, M, G, Ci, Co, precision=0):
-        key = (w.data_ptr(), w._version, w.device, op, L, G, Ci, Co, precision)
-        if self.enabled and self._key == key and self._packed is not None:
+        try:
+            version = w._version
+        except RuntimeError:     # inference-mode tensors have no version counter: never reuse
+            version = None
+        key = (w.data_ptr(), version, w.device, op, L, G, Ci, Co, precision)
+        same = self._ref is not None and self._ref() is w
+        if self.enabled and version is not None and same and self._key == key and self._packed is not None:
             return self._packed
         n = int(_lib.load().b200sht_mix_weight_elems(op, L, M, G, Ci, Co))
         packed = torch.empty(n, dtype=torch.float32, device=w.device)
         wc = w.detach().contiguous()
         _lib.call("b200sht_mix_weight_pack", op, _ptr(wc), _ptr(packed), L, G, Ci, Co, precision, _stream(w.device))
         self._key, self._packed = key, packed
+        try:
+            self._ref = weakref.ref(w)
+        except TypeError:
+            self._ref = None
         return packed
 
 
@@ -260,6 +277,18 @@ class SpectralConv(nn.Module):
         self._wcache = PackedWeightCache()
         self.one_call = True   # False: one autograd node per stage (same kernels; used by the distributed transforms)
 
+    def invalidate_weight_cache(self):
+        """after writes to `weight` that bypass the version counter (`weight.data.copy_`, custom kernels)"""
+        self._wcache.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):           # .to() / .cuda() / .float(): the parameter storage changes
+        self._wcache.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._wcache.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def forward(self, x):
         dtype = x.dtype
         residual = x
@@ -411,6 +440,18 @@ class SpectralAttention(nn.Module):
         self.modes_lat_local = getattr(inverse_transform, "lmax_local", self.modes_lat)
         self.modes_lon_local = getattr(inverse_transform, "mmax_local", self.modes_lon)
         self._dense = _lib.DENSE_FLAG if getattr(inverse_transform, "packed_dense", False) else 0
+
+    def invalidate_weight_cache(self):
+        for c in self._caches:
+            c.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_weight_cache()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_weight_cache()
+        return super()._load_from_state_dict(*args, **kwargs)
         if operator_type == "l-dependant" and self.modes_lat_local != self.modes_lat:
             raise ValueError("SpectralAttention(operator_type='l-dependant') with an l-sharded transform (h_parallel_size > 1) is not supported: "
                              "its weights are indexed by the global degree")

@@ -267,6 +267,18 @@ def test_weight_cache_tracks_parameter_updates():
         conv.weight.mul_(2.0)
     y1, _ = conv(x)
     close(y1, 2 * y0, 1e-6, "cached packed weight follows in-place parameter updates")
+    packed = conv._wcache._packed
+    conv(x)
+    assert conv._wcache._packed is packed, "an unchanged parameter must reuse the packed copy"
+    conv.weight.data.mul_(0.5)            # bypasses the version counter: needs an explicit invalidation
+    conv.invalidate_weight_cache()
+    y2, _ = conv(x)
+    close(y2, y0, 1e-6, "invalidate_weight_cache after a .data write")
+    sd = {k: v.clone() for k, v in conv.state_dict().items()}
+    sd["weight"] = sd["weight"] * 3.0
+    conv.load_state_dict(sd)
+    y3, _ = conv(x)
+    close(y3, 3 * y0, 1e-6, "load_state_dict invalidates the packed copy")
 
 
 # ------------------------------------------------------------------- contractions / activations vs reference golden
