@@ -171,6 +171,10 @@ int b200sht_mix_weight_unpack(int op, const float* w_packed, void* w_native, int
  * cbias (OP_SHARED / OP_LDEP only, may be null): complex64 [Co] added to every mode (compl_muladd2d_fwd). */
 int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, const void* cbias,
                         float* y, int B, int G, int Ci, int Co, int precision, void* stream);
+/* 1 when b200sht_mix_forward / _backward run this shape on the tensor cores at `precision`, 0 when they run the fp32 CUDA-core
+ * kernels: B200SHT_PREC_TF32 needs a dense operator, a batch that divides 32 and 16-byte aligned group slices; anything else is
+ * served in fp32 -- the caller should then pack the weight with B200SHT_PREC_FP32 (no TF32 rounding) and may want to tell the user. */
+int b200sht_mix_uses_tensor_cores(int op, int B, int G, int Ci, int Co, int precision);
 /* gx = dL/dx (may be null), gw = dL/dw in the same format as w (may be null; overwritten, not accumulated),
  * gcbias complex64 [Co] (may be null). */
 int b200sht_mix_backward(int L, int M, int op, const float* x, const void* w, const float* gy,

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b200sht_mix_weight_elems": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b200sht_mix_weight_pack": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200sht_mix_weight_unpack": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200sht_mix_uses_tensor_cores": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b200sht_mix_forward": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200sht_mix_backward": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200sht_complex_relu_forward": (c_int, [c_int, c_int, c_int, _P, _P, c_float, _P, c_int, c_int, _P]),

@@ -396,6 +396,11 @@ static bool umma_mix_shape(int B, int G, int Ci, int Co) {
   return B >= 1 && 32 % B == 0 && (G == 1 || ((Ci / G) % 4 == 0 && (Co / G) % 4 == 0));
 }
 
+int b200sht_mix_uses_tensor_cores(int op, int B, int G, int Ci, int Co, int precision) {
+  if (G <= 0 || Ci % G != 0 || Co % G != 0) return 0;
+  return (precision == B200SHT_PREC_TF32 && dense_op(op & 0xff) && umma_mix_shape(B, G, Ci, Co)) ? 1 : 0;
+}
+
 int b200sht_mix_forward(int L, int M, int op, const float* x, const void* w, const void* cbias, float* y, int B, int G, int Ci, int Co,
                         int precision, void* stream) {
   B200_REQUIRE(L > 0 && M > 0 && x && w && y, "mix_forward: bad argument");

@@ -511,13 +511,21 @@ struct MixWgradTraits {
 };
 
 // ================================================================================================== host side
-static int g_umma_ok = -1;
+// per device (a process may hold tensors on several GPUs): -1 unknown, 0 / 1
+constexpr int kMaxDevices = 64;
+static int g_umma_ok[kMaxDevices];
+static int g_sm_count[kMaxDevices];
+static std::once_flag g_dev_once;
+static void init_dev_caches() { for (int i = 0; i < kMaxDevices; ++i) { g_umma_ok[i] = -1; g_sm_count[i] = 0; } }
 int umma_available() {
-  if (g_umma_ok >= 0) return g_umma_ok;
+  std::call_once(g_dev_once, init_dev_caches);
   int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
-  g_umma_ok = (major == 10 && get_encode() != nullptr) ? 1 : 0;
-  return g_umma_ok;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < kMaxDevices && g_umma_ok[dev] >= 0) return g_umma_ok[dev];
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  const int ok = (major == 10 && get_encode() != nullptr) ? 1 : 0;
+  if (dev >= 0 && dev < kMaxDevices) g_umma_ok[dev] = ok;
+  return ok;
 }
 
 int round_table_tf32(const float* src, float* dst, size_t n, cudaStream_t st);  // legendre.cu
@@ -579,12 +587,13 @@ static void set_accumulators(EngineParams* e, int cols) {
   e->tmem_cols = tmem_cols_pow2(e->acc_cols * e->nbuf);
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+static int sm_count() {   // of the current device (the launch device: _lib.call makes the tensor's device current)
+  std::call_once(g_dev_once, init_dev_caches);
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDevices && g_sm_count[dev] > 0) return g_sm_count[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < kMaxDevices) g_sm_count[dev] = n;
   return n;
 }
 

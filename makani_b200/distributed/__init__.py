@@ -144,7 +144,7 @@ def _p(t):
 
 
 def _st(dev):
-    return L.launch_stream(dev)
+    return _lib().launch_stream(dev)
 
 
 def _dt(dtype):

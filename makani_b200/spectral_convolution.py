@@ -10,6 +10,7 @@ The whole forward is 5 kernels: longitude FFT -> Legendre analysis -> channel mi
 """
 import ctypes
 import math
+import warnings
 
 import weakref
 
@@ -31,6 +32,27 @@ def _op_code(operator_type, separable):
     if operator_type == "diagonal":
         return _lib.OP_SEP_DIAGONAL if separable else _lib.OP_DIAGONAL
     raise ValueError(f"Unknown operator type {operator_type}")
+
+
+_warned_mix_fallback = set()
+
+
+def mix_pack_precision(op, B, G, Ci, Co, precision):
+    """Precision the packed weight must be prepared for.  The tcgen05 channel mix (precision tf32) needs a batch that divides 32 and
+    16-byte aligned group slices; other shapes are served by the fp32 CUDA-core kernels (correct, slower).  In that case the weight is NOT
+    rounded to TF32 (the result is then plain fp32, not a mixture) and the user is told once per shape."""
+    if precision != _lib.PREC_TF32:
+        return precision
+    if int(_lib.load().b200sht_mix_uses_tensor_cores(op & 0xFF, B, G, Ci, Co, precision)):
+        return precision
+    key = (B, G, Ci, Co)
+    if key not in _warned_mix_fallback:
+        _warned_mix_fallback.add(key)
+        warnings.warn(
+            f"makani_b200: the tensor-core channel mix needs a per-GPU batch that divides 32 and group slices that are multiples of 4 channels; "
+            f"batch {B}, groups {G}, channels {Ci}->{Co} runs the fp32 CUDA-core mix instead (slower; the SHT stages stay on the tensor cores)",
+            RuntimeWarning, stacklevel=3)
+    return _lib.PREC_FP32
 
 
 class PackedWeightCache:
@@ -80,7 +102,7 @@ class _MixPacked(torch.autograd.Function):
             raise B200ShtError(f"spectral weights must be complex64, got {weight.dtype}")
         base_op = op & 0xFF  # op may carry _lib.DENSE_FLAG (l/m-sharded spectra of the distributed path)
         if base_op in _DENSE_OPS:
-            wdev = (cache if cache is not None else PackedWeightCache()).get(weight, base_op, L, M, G, Ci, Co, precision)
+            wdev = (cache if cache is not None else PackedWeightCache()).get(weight, base_op, L, M, G, Ci, Co, mix_pack_precision(base_op, B, G, Ci, Co, precision))
         else:
             wdev = weight.detach().contiguous()
         y = torch.empty(int(_lib.load().b200sht_spec_elems_lm(L, M, B, Co)), dtype=torch.float32, device=dev)
@@ -143,7 +165,8 @@ class _SpectralConvOneCall(torch.autograd.Function):
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         L, M = mod.modes_lat_local, mod.modes_lon_local
         if op in _DENSE_OPS:
-            wdev = mod._wcache.get(weight, op, L, M, mod.num_groups, mod.in_channels, mod.out_channels, prec)
+            wdev = mod._wcache.get(weight, op, L, M, mod.num_groups, mod.in_channels, mod.out_channels,
+                                   mix_pack_precision(op, B, mod.num_groups, mod.in_channels, mod.out_channels, prec))
         else:
             wdev = weight.detach().contiguous()
         spec_saved = torch.empty(pf.spec_elems(B, mod.in_channels), dtype=torch.float32, device=dev)
@@ -440,6 +463,9 @@ class SpectralAttention(nn.Module):
         self.modes_lat_local = getattr(inverse_transform, "lmax_local", self.modes_lat)
         self.modes_lon_local = getattr(inverse_transform, "mmax_local", self.modes_lon)
         self._dense = _lib.DENSE_FLAG if getattr(inverse_transform, "packed_dense", False) else 0
+        if operator_type == "l-dependant" and self.modes_lat_local != self.modes_lat:
+            raise ValueError("SpectralAttention(operator_type='l-dependant') with an l-sharded transform (h_parallel_size > 1) is not supported: "
+                             "its weights are indexed by the global degree")
 
     def invalidate_weight_cache(self):
         for c in self._caches:
@@ -452,9 +478,6 @@ class SpectralAttention(nn.Module):
     def _load_from_state_dict(self, *args, **kwargs):
         self.invalidate_weight_cache()
         return super()._load_from_state_dict(*args, **kwargs)
-        if operator_type == "l-dependant" and self.modes_lat_local != self.modes_lat:
-            raise ValueError("SpectralAttention(operator_type='l-dependant') with an l-sharded transform (h_parallel_size > 1) is not supported: "
-                             "its weights are indexed by the global degree")
 
     def _mlp_packed(self, h, B):
         if self.training and self.drop_rate > 0.0:
