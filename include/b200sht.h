@@ -238,6 +238,11 @@ int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float
 /* wait-time profile of the tensor-core DFT kernels (environment B200SHT_DFT_PROF=1): 16 counters of SM clocks, accumulated over all launches since the
  * last call and cleared by it (slots: see csrc/dft.cu).  All zeros when the profile is off.  Synchronises the device. */
 int b200sht_debug_dft_profile(uint64_t* counters16);
+/* Latitude chunks of the fused (longitude analysis -> Legendre analysis) pair inside b200sht_sht_forward / _inverse_adjoint and the
+ * SpectralConv entry points at B200SHT_PREC_TF32: n > 1 forces n chunks, 1 switches chunking off, 0 restores the default (by size; the
+ * environment variable B200SHT_LAT_CHUNKS sets the initial value).  Returns the previous setting.  Results are identical up to the
+ * summation order of the Legendre sums. */
+int b200sht_debug_set_lat_chunks(int n);
 /* radices chosen for length N; returns the number of stages or a negative status */
 int b200sht_debug_fft_plan(int N, int* radices, int max_radices);
 /* table [mmax][lmax][nlat] (fp32) from cos(colatitude) cost[nlat] */

@@ -44,7 +44,9 @@ int dft_plan_init(Plan* pl);
 void dft_plan_destroy(Plan* pl);
 int dft_host(int N, int mmax, int direction, int mode, const float* rowscale, const float* in, float* out);
 int dft_profile_read(unsigned long long* out16);
-int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo = nullptr);
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo = nullptr, int k_begin = 0,
+                           int k_end = -1, int accumulate = 0, int last = 1);
+int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int mode, int round_tf32, cudaStream_t st, int k_begin = 0, int k_end = -1);
 int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo = nullptr);
 int umma_plan_table_lo(const Plan* pl);
 int tf32_residual(const float* src, float* dst, size_t n, cudaStream_t st);
@@ -278,6 +280,48 @@ static int synthesis_pair(const b200sht_plan* pl, const float* spec, float* lat,
   return rc;
 }
 
+// Longitude analysis + Legendre analysis.  At TF32 with the tensor-core DFT the pair can run in latitude chunks: the DFT writes the latspec
+// rows of one chunk (tens of MB) and the Legendre kernel reduces over exactly those rows right away -- reading them from the 126 MB L2
+// instead of HBM -- and adds its partial sums to the coefficients of the earlier chunks (unrounded fp32; the last chunk rounds to TF32).
+// The Legendre table is sliced along latitude, so no byte of it is read twice.  B200SHT_LAT_CHUNKS = n forces n chunks (1 = off);
+// default: chunks of at most kLatChunkBytes of latspec when the whole tensor exceeds it.
+constexpr size_t kLatChunkBytes = 40u << 20;
+constexpr bool kLatChunkByDefault = false;   // see DESIGN.md section 10 for the measurement behind this
+static int& lat_chunks_forced() {
+  static int forced = [] { const char* e = getenv("B200SHT_LAT_CHUNKS"); return e ? atoi(e) : 0; }();
+  return forced;
+}
+static int lat_chunks(const b200sht_plan* pl, int B, int C) {
+  int n = lat_chunks_forced();
+  if (n <= 0 && !kLatChunkByDefault) return 1;
+  if (n <= 0) {
+    const size_t bytes = (size_t)pl->mmax * 2 * B * C * pl->kp * sizeof(float);
+    n = (int)((bytes + kLatChunkBytes - 1) / kLatChunkBytes);
+  }
+  const int maxn = pl->nlat / 64;   // at least two 32-row K-blocks per chunk
+  if (n > maxn) n = maxn;
+  return n < 1 ? 1 : n;
+}
+static int analysis_pair(const b200sht_plan* pl, const void* x, int dtype, int B, int C, float* lat, float* spec, int mode, int precision, void* stream) {
+  const bool dft = precision == B200SHT_PREC_TF32 && pl->umma_ok && !pl->no_table && dft_usable(pl) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (dtype == B200SHT_BF16 || pl->nlon % 32 == 0);
+  const int n = dft ? lat_chunks(pl, B, C) : 1;
+  if (n <= 1) {
+    int rc = b200sht_fft_analysis(pl, x, dtype, B, C, lat, mode | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
+    if (!rc) rc = b200sht_legendre_analysis(pl, lat, spec, B, C, precision, stream);
+    return rc;
+  }
+  B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "analysis: B*C=%lld out of range", (long long)B * C);
+  const int rows = round_up(ceil_div(pl->nlat, n), 32);
+  int rc = 0;
+  for (int k0 = 0, i = 0; k0 < pl->nlat && !rc; k0 += rows, ++i) {
+    const bool last = k0 + rows >= pl->nlat;
+    rc = dft_analysis(pl, x, dtype, B, C, lat, mode & 1, 1, S(stream), k0, last ? -1 : k0 + rows);
+    if (!rc) rc = legendre_analysis_umma(pl, lat, spec, B, C, S(stream), nullptr, k0, last ? -1 : k0 + rows, i > 0, last);
+  }
+  return rc;
+}
+
 int b200sht_spec_unpack(int L, int M, const float* spec, void* coeffs, int B, int C, void* stream) {
   B200_REQUIRE(L > 0 && M > 0 && spec && coeffs, "spec_unpack: bad argument");
   Plan p = lm_plan(L, M);
@@ -329,8 +373,7 @@ int b200sht_sht_forward(const b200sht_plan* pl, const void* x, int dtype, int B,
   B200_REQUIRE(pl && x && coeffs && ws, "sht_forward: null argument");
   float *X, *sp;
   split_ws(pl, B, C, ws, &X, &sp);
-  int rc = b200sht_fft_analysis(pl, x, dtype, B, C, X, 0 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
-  if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
+  int rc = analysis_pair(pl, x, dtype, B, C, X, sp, 0, precision, stream);
   if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, coeffs, B, C, stream);
   return rc;
 }
@@ -359,8 +402,7 @@ int b200sht_sht_inverse_adjoint(const b200sht_plan* pl, const void* gy, int dtyp
   B200_REQUIRE(pl && gy && gcoeffs && ws, "sht_inverse_adjoint: null argument");
   float *X, *sp;
   split_ws(pl, B, C, ws, &X, &sp);
-  int rc = b200sht_fft_analysis(pl, gy, dtype, B, C, X, 1 | (precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
-  if (!rc) rc = b200sht_legendre_analysis(pl, X, sp, B, C, precision, stream);
+  int rc = analysis_pair(pl, gy, dtype, B, C, X, sp, 1, precision, stream);
   if (!rc) rc = b200sht_spec_unpack(pl->lmax, pl->mmax, sp, gcoeffs, B, C, stream);
   return rc;
 }
@@ -481,8 +523,7 @@ int b200sht_spectral_conv_forward(const b200sht_plan* f, const b200sht_plan* v, 
   B200_REQUIRE(x && w && y && workspace, "spectral_conv_forward: null argument");
   ConvWs ws = conv_ws(f, v, d, workspace);
   float* spec_x = spec_x_saved ? spec_x_saved : ws.spec_in;
-  rc = b200sht_fft_analysis(f, x, d->dtype, d->B, d->Cin, ws.lat_in, 0 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
-  if (!rc) rc = b200sht_legendre_analysis(f, ws.lat_in, spec_x, d->B, d->Cin, d->precision, stream);
+  rc = analysis_pair(f, x, d->dtype, d->B, d->Cin, ws.lat_in, spec_x, 0, d->precision, stream);
   if (!rc && residual) {
     rc = synthesis_pair(v, spec_x, ws.lat_out, residual, d->dtype, d->B, d->Cin, nullptr, 0, d->precision, stream);
   }
@@ -511,9 +552,8 @@ int b200sht_spectral_conv_backward_ex(const b200sht_plan* f, const b200sht_plan*
   B200_REQUIRE(gw == nullptr || spec_x_saved != nullptr, "spectral_conv_backward: weight gradient needs the saved spectrum");
   ConvWs ws = conv_ws(f, v, d, workspace);
   // dL/d(spec_out) = analysis_v(fft_v(gy, adjoint scaling))
-  rc = b200sht_fft_analysis(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
-  if (!rc && gbias) rc = b200sht_bias_grad(v, ws.lat_out, gbias, d->B, d->Cout, stream);
-  if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cout, d->precision, stream);
+  rc = analysis_pair(v, gy, d->dtype, d->B, d->Cout, ws.lat_out, ws.spec_out, 1, d->precision, stream);
+  if (!rc && gbias) rc = b200sht_bias_grad(v, ws.lat_out, gbias, d->B, d->Cout, stream);   // the m = 0 plane of the complete latspec
   // with an event to signal, the weight gradient goes first and the input gradient of the mix joins the overlapped stages below
   const bool split_mix = wgrad_ready_event != nullptr && gw != nullptr && gx != nullptr;
   if (!rc) rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, (gx && !split_mix) ? ws.spec_in : nullptr, gw, nullptr, d->B, d->G,
@@ -539,8 +579,7 @@ int b200sht_spectral_conv_backward_ex(const b200sht_plan* f, const b200sht_plan*
     rc = b200sht_mix_backward(f->lmax, f->mmax, d->op, spec_x_saved, w, ws.spec_out, ws.spec_in, nullptr, nullptr, d->B, d->G, d->Cin, d->Cout, d->precision, stream);
   if (!rc && gx) {
     if (gresidual) {
-      rc = b200sht_fft_analysis(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, 1 | (d->precision == B200SHT_PREC_TF32 ? 2 : 0), stream);
-      if (!rc) rc = b200sht_legendre_analysis(v, ws.lat_out, ws.spec_out, d->B, d->Cin, d->precision, stream);
+      rc = analysis_pair(v, gresidual, d->dtype, d->B, d->Cin, ws.lat_out, ws.spec_out, 1, d->precision, stream);
       if (!rc) {
         const long long n = b200sht_spec_elems(f, d->B, d->Cin);
         axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(ws.spec_in, ws.spec_out, n);
@@ -578,6 +617,12 @@ int b200sht_spectral_conv_forward_host(const b200sht_plan* f, const b200sht_plan
     return B200SHT_ERR_CUDA;
   }
   return rc;
+}
+
+int b200sht_debug_set_lat_chunks(int n) {
+  const int old = lat_chunks_forced();
+  lat_chunks_forced() = n;
+  return old;
 }
 
 int b200sht_debug_dft_profile(uint64_t* counters16) {

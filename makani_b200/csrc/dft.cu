@@ -522,6 +522,7 @@ struct DftAnaParams {
   const float* rowscale;
   unsigned long long* prof;
   int R, nlat, nlon, kp, mmax, N2, half, M2, nkb, mode, round_tf32, ntiles, ktiles, nraw, gs;
+  int kt0;   // first 16-row tile of the latitude range this launch transforms (ktiles = tiles in the range; latitude-chunked analysis, capi.cu)
   uint32_t idesc, idesc_neg;
 };
 
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     if (lane == 0) {
       int n = 0;
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-        const int r = ti / p.ktiles, row0 = r * p.nlat + (ti - r * p.ktiles) * 16;
+        const int r = ti / p.ktiles, row0 = r * p.nlat + (p.kt0 + ti - r * p.ktiles) * 16;
         for (int kb = 0; kb < nkb; ++kb) {
           const int g = n * nkb + kb, rs = g % p.nraw, it = g / p.nraw;
           if (it > 0) prof_wait(prof, 2, &raw_empty[rs], (it - 1) & 1, true);
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     const size_t plane = (size_t)p.R * p.kp;
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 16;
+      const int r = ti / p.ktiles, k0 = (p.kt0 + ti - r * p.ktiles) * 16;
       const int k = k0 + kr;
       const int buf = n & 3, use = n >> 2;
       const bool kok = k < p.kp;
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
     const T* const rawS = reinterpret_cast<const T*>(gR);
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-      const int r = ti / p.ktiles, kt16 = (ti - r * p.ktiles) * 16;
+      const int r = ti / p.ktiles, kt16 = (p.kt0 + ti - r * p.ktiles) * 16;
       for (int ii = 0; ii < ipw; ++ii) {
         const int item = pw + ii * nprod;
         const int kb = item >> 3, q = item & 7;
@@ -811,7 +812,8 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
-int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int mode, int round_tf32, cudaStream_t st) {
+// k_begin / k_end: latitude range [k_begin, k_end) to transform (k_begin a multiple of 16; k_end < 0: up to kp) -- the other rows of X are not touched
+int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int mode, int round_tf32, cudaStream_t st, int k_begin, int k_end) {
   const DftTables* t = static_cast<const DftTables*>(pl->dft_state);
   B200_REQUIRE(t != nullptr, "dft_analysis: plan has no DFT tables");
   const int R = B * C;
@@ -820,7 +822,10 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   p.X = X; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.prof = dft_prof_buffer();
   p.R = R; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.M2 = t->M2; p.nkb = t->nkb; p.mode = mode; p.round_tf32 = round_tf32;
-  p.ktiles = (pl->kp + 15) / 16; p.ntiles = R * p.ktiles;
+  if (k_end < 0 || k_end > pl->kp) k_end = pl->kp;
+  B200_REQUIRE(k_begin >= 0 && k_begin % 16 == 0 && k_begin < k_end, "dft_analysis: bad latitude range [%d, %d)", k_begin, k_end);
+  p.kt0 = k_begin / 16;
+  p.ktiles = (k_end - k_begin + 15) / 16; p.ntiles = R * p.ktiles;
   const bool bf16 = (dtype == B200SHT_BF16);
   p.nraw = bf16 ? 3 : 2;   // raw stages of 20 / 34 KB
   p.idesc = make_idesc(32, 0, 0, 0);

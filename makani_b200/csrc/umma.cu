@@ -139,6 +139,8 @@ struct AnaTraits {
     alignas(64) CUtensorMap tmA_lo, tmB_lo;   // residuals of the table and of X (split mode)
     float* spec;
     int L, M, nlat, C, cp, PB, Cc, PBc, n_ct, N, m0;
+    int kb0, nkb;        // latitude range of this launch in 32-row K-blocks (latitude-chunked analysis: partial sums over a chunk of rows)
+    int acc_in, round_out;   // add to the spec values already stored (chunks after the first) / round the result to TF32 (last chunk)
     uint32_t idesc;
   };
   struct Tile { int m, l0, c0, pb0; };
@@ -150,8 +152,9 @@ struct AnaTraits {
     return t.l0 < p.L;
   }
   __device__ static void prefetch(const Params& p) { prefetch_tmap(&p.tmA); prefetch_tmap(&p.tmB); }
-  __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.nlat + 31) / 32; }
+  __device__ static int num_kblocks(const Params& p, const Tile&) { return p.nkb; }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint32_t st, uint64_t* bar) {
+    kb += p.kb0;
     tma_load_3d(st, &p.tmA, bar, kb * 32, t.l0, t.m);
     tma_load_4d(st + 16384, &p.tmB, bar, kb * 32, t.c0, t.pb0, t.m);
     if (p.split) {
@@ -187,10 +190,16 @@ struct AnaTraits {
         const int pbi = n / p.Cc, ci = n - pbi * p.Cc;
         const int pb = t.pb0 + pbi, c = t.c0 + ci;
         if (pb < p.PB && c < p.cp) {
-          if (p.split)   // strict fp32: the coefficients stay as accumulated
-            *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          else           // consumers are kind::tf32 MMAs: round to nearest here
-            *reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c) = make_float4(tf32_rn(v[q * 4]), tf32_rn(v[q * 4 + 1]), tf32_rn(v[q * 4 + 2]), tf32_rn(v[q * 4 + 3]));
+          float4* dst = reinterpret_cast<float4*>(orow + (size_t)pb * p.cp + c);
+          float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          if (p.acc_in) {   // partial sums of the earlier latitude chunks (unrounded fp32)
+            const float4 old = *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          // strict fp32 (split) and the partial sums of a chunked analysis stay as accumulated; otherwise the consumers are kind::tf32
+          // MMAs: round to nearest here
+          if (p.round_out) o = make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w));
+          *dst = o;
         }
       }
     }
@@ -616,9 +625,18 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------- Legendre
-int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo) {
+// k_begin / k_end: latitude range [k_begin, k_end) to reduce over (k_begin a multiple of 32; k_end < 0: all rows); accumulate: add to the spec
+// values stored by the launches of the earlier ranges; last: this is the final range (TF32 rounding of the result happens here)
+int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo, int k_begin, int k_end,
+                           int accumulate, int last) {
   AnaTraits::Params p;
   memset(&p, 0, sizeof(p));
+  if (k_end < 0 || k_end > pl->nlat) k_end = pl->nlat;
+  B200_REQUIRE(k_begin >= 0 && k_begin % 32 == 0 && k_begin < k_end, "legendre_analysis: bad latitude range [%d, %d)", k_begin, k_end);
+  p.kb0 = k_begin / 32;
+  p.nkb = ceil_div(k_end - k_begin, 32);
+  p.acc_in = accumulate;
+  p.round_out = (last && X_lo == nullptr) ? 1 : 0;
   const int cp = round_up(C, 4), PB = 2 * B;
   p.spec = spec; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.C = C; p.cp = cp; p.PB = PB; p.m0 = pl->m0;
   if (cp <= 128) { p.Cc = cp; p.n_ct = 1; p.PBc = 256 / cp < PB ? 256 / cp : PB; }

@@ -40,3 +40,25 @@ def test_benched_block_strict_fp32():
     print(f"[benched] sfno_block_721x1440x73 fp32 rel_l2: {rel}")
     for k, v in rel.items():
         assert v < 5e-6, (k, rel)
+
+
+@pytest.mark.parametrize("chunks", [2, 3])
+def test_benched_block_latitude_chunked_analysis(chunks):
+    """The latitude-chunked (longitude analysis -> Legendre analysis) pair (b200sht_debug_set_lat_chunks): same
+    tolerances against the oracle as the unchunked path, and agreement with it up to the summation order of the Legendre sums."""
+    from makani_b200 import _lib
+
+    lib = _lib.load()
+    old = lib.b200sht_debug_set_lat_chunks(1)
+    try:
+        ref = _run_conv_case(CFG_2C, "tf32", 1e-3, act_dtype=torch.float32, return_outputs=True)
+        lib.b200sht_debug_set_lat_chunks(chunks)
+        got = _run_conv_case(CFG_2C, "tf32", 1e-3, act_dtype=torch.float32, return_outputs=True)
+    finally:
+        lib.b200sht_debug_set_lat_chunks(old)
+    for k in ref[1]:
+        a, b = got[1][k].double(), ref[1][k].double()
+        d = float((a - b).norm() / b.norm())
+        print(f"[chunked x{chunks}] {k}: rel_l2 vs unchunked {d:.2e}, vs oracle {got[0][k]:.2e} (unchunked {ref[0][k]:.2e})")
+        assert d < 2e-4, (k, d)
+        assert got[0][k] < 1e-3, (k, got[0])
