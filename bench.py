@@ -467,6 +467,8 @@ def run_gpu_arm(args):
         except Exception as e:  # noqa: BLE001
             return {"ok": False, "why": str(e)[:300]}
 
+    host_enqueue = {}
+
     def timed(fn, steps, warmup, use_flush=True):
         for _ in range(warmup):
             fn()
@@ -474,6 +476,7 @@ def run_gpu_arm(args):
         if world > 1:
             dist.barrier()
         evs = []
+        t_host = time.perf_counter()
         for _ in range(steps):
             if use_flush:
                 flush.zero_()
@@ -482,6 +485,7 @@ def run_gpu_arm(args):
             fn()
             e1.record()
             evs.append((e0, e1))
+        host_enqueue["ms_per_step"] = (time.perf_counter() - t_host) * 1e3 / steps   # host time to ENQUEUE a step (no synchronisation inside the loop)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -528,6 +532,7 @@ def run_gpu_arm(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev = None
+    host_ms = None
     try:
         dp_step()  # first call builds plans / tables
         torch.cuda.synchronize()
@@ -545,6 +550,7 @@ def run_gpu_arm(args):
                 step(x_dev)  # local load only: no collective here, the other ranks are waiting at the next barrier
                 torch.cuda.synchronize()
         ms_dev = timed(dp_step, args.steps, args.warmup)
+        host_ms = host_enqueue.get("ms_per_step")
         # opt-in (round-2 experiment, not part of the default line): the same step replayed from a CUDA graph, reported separately
         if args.graph and world == 1:
             graph_info = try_cuda_graph()
@@ -689,6 +695,9 @@ def run_gpu_arm(args):
                 "serial_value": world * 1e3 / ms_e2e_serial, "serial_ms_per_step": ms_e2e_serial,
                 "serial_how": "copy -> fwd+bwd -> read-back in one stream, L2 flushed between steps"},
         "gpu_launches": launches_per_step,
+        # host time to enqueue one step (Python + ctypes + tensor-map encodes + launches), measured around the timed loop: when it is not well
+        # below ms_per_step the step is launch-bound on this host and cuda_graph_replay (--graph) is the device-bound number
+        "host_enqueue_ms_per_step": host_ms,
         "roofline": roof,
         "roofline_stages": stages,
         "cpu_baseline": cpu,

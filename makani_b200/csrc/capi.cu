@@ -47,7 +47,9 @@ int dft_profile_read(unsigned long long* out16);
 int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, int C, cudaStream_t st, const float* X_lo = nullptr, int k_begin = 0,
                            int k_end = -1, int accumulate = 0, int last = 1);
 int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* X, int mode, int round_tf32, cudaStream_t st, int k_begin = 0, int k_end = -1);
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo = nullptr);
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo = nullptr,
+                            int k_begin = 0, int k_end = -1);
+int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int mode, cudaStream_t st, int k_begin = 0, int k_end = -1);
 int umma_plan_table_lo(const Plan* pl);
 int tf32_residual(const float* src, float* dst, size_t n, cudaStream_t st);
 bool dft_usable(const Plan* pl);
@@ -267,19 +269,6 @@ int b200sht_legendre_synthesis_tiled(const b200sht_plan* pl, const float* spec, 
   return legendre_synthesis_umma(pl, spec, latspec, B, C, 1, S(stream));
 }
 
-// Legendre synthesis + longitude synthesis: through the tiled latspec layout and the tensor-core DFT when the plan supports it at TF32
-static int synthesis_pair(const b200sht_plan* pl, const float* spec, float* lat, void* y, int dtype, int B, int C, const float* bias, int mode,
-                          int precision, void* stream) {
-  if (precision == B200SHT_PREC_TF32 && pl->umma_ok && dft_usable(pl)) {
-    int rc = b200sht_legendre_synthesis_tiled(pl, spec, lat, B, C, stream);
-    if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode | 2, stream);
-    return rc;
-  }
-  int rc = b200sht_legendre_synthesis(pl, spec, lat, B, C, precision, stream);
-  if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode, stream);
-  return rc;
-}
-
 // Longitude analysis + Legendre analysis.  At TF32 with the tensor-core DFT the pair can run in latitude chunks: the DFT writes the latspec
 // rows of one chunk (tens of MB) and the Legendre kernel reduces over exactly those rows right away -- reading them from the 126 MB L2
 // instead of HBM -- and adds its partial sums to the coefficients of the earlier chunks (unrounded fp32; the last chunk rounds to TF32).
@@ -290,6 +279,12 @@ constexpr bool kLatChunkByDefault = false;   // see DESIGN.md section 10 for the
 static int& lat_chunks_forced() {
   static int forced = [] { const char* e = getenv("B200SHT_LAT_CHUNKS"); return e ? atoi(e) : 0; }();
   return forced;
+}
+// the synthesis pair (Legendre synthesis -> longitude synthesis) can be chunked the same way (B200SHT_LAT_CHUNKS_SYN = n; off by default):
+// its consumer, the DFT kernel, is not HBM-bound, so the gain is the latency of L2 hits only
+static int lat_chunks_syn() {
+  static const int n = [] { const char* e = getenv("B200SHT_LAT_CHUNKS_SYN"); return e ? atoi(e) : 0; }();
+  return n;
 }
 static int lat_chunks(const b200sht_plan* pl, int B, int C) {
   int n = lat_chunks_forced();
@@ -302,6 +297,31 @@ static int lat_chunks(const b200sht_plan* pl, int B, int C) {
   if (n > maxn) n = maxn;
   return n < 1 ? 1 : n;
 }
+// Legendre synthesis + longitude synthesis: through the tiled latspec layout and the tensor-core DFT when the plan supports it at TF32
+static int synthesis_pair(const b200sht_plan* pl, const float* spec, float* lat, void* y, int dtype, int B, int C, const float* bias, int mode,
+                          int precision, void* stream) {
+  if (precision == B200SHT_PREC_TF32 && pl->umma_ok && dft_usable(pl)) {
+    const int n = lat_chunks_syn();
+    if (n > 1 && pl->kp > 128 && (reinterpret_cast<uintptr_t>(lat) & 127) == 0) {
+      B200_REQUIRE(B > 0 && C > 0 && (long long)B * C <= 65535, "synthesis: B*C=%lld out of range", (long long)B * C);
+      const int rows = round_up(ceil_div(pl->kp, n), 128);
+      int rc = 0;
+      for (int k0 = 0; k0 < pl->kp && !rc; k0 += rows) {
+        const int k1 = k0 + rows < pl->kp ? k0 + rows : -1;
+        rc = legendre_synthesis_umma(pl, spec, lat, B, C, 1, S(stream), nullptr, k0, k1);
+        if (!rc) rc = dft_synthesis(pl, lat, y, dtype, B, C, bias, mode & 1, S(stream), k0, k1);
+      }
+      return rc;
+    }
+    int rc = b200sht_legendre_synthesis_tiled(pl, spec, lat, B, C, stream);
+    if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode | 2, stream);
+    return rc;
+  }
+  int rc = b200sht_legendre_synthesis(pl, spec, lat, B, C, precision, stream);
+  if (!rc) rc = b200sht_fft_synthesis(pl, lat, y, dtype, B, C, bias, mode, stream);
+  return rc;
+}
+
 static int analysis_pair(const b200sht_plan* pl, const void* x, int dtype, int B, int C, float* lat, float* spec, int mode, int precision, void* stream) {
   const bool dft = precision == B200SHT_PREC_TF32 && pl->umma_ok && !pl->no_table && dft_usable(pl) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                    (dtype == B200SHT_BF16 || pl->nlon % 32 == 0);

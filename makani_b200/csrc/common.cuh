@@ -82,6 +82,21 @@ struct Plan {
 // run, the collective then lands between two kernels and the next one starts on fewer SMs with a static tile assignment -- slower than
 // giving the SMs away up front.
 int& sm_reserve();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) and size increase instead of before every launch: the call takes
+// the context lock and was a measurable part of the host time per launch (13 launches per SpectralConv step).  One cache per kernel
+// instantiation (the template parameter is the call site's tag type).
+template <class Tag, class K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes) {
+  static int granted[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && (size_t)granted[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = (int)bytes;
+  return e;
+}
 inline int usable_sms(int sms) { const int r = sm_reserve(); return (r > 0 && sms - r >= 1) ? sms - r : sms; }
 
 }  // namespace b200sht

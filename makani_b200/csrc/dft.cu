@@ -242,6 +242,7 @@ struct DftSynParams {
   void* trash;
   unsigned long long* prof;
   int R, C, nlat, nlon, kp, mmax, N2, half, M2, qpr, nrep, mode, ntiles, ktiles, has_nyq;
+  int kt0, kt_all;   // latitude range of this launch: first 8-row tile, tiles per image in the whole tensor (ktiles = tiles per image in the range)
   uint32_t idesc;
 };
 
@@ -299,10 +300,11 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
         if (it > 0) prof_wait(prof, 8, &empty[s], (it - 1) & 1, true);
         mbar_expect_tx(&full[s], 16384);
         const uint32_t st = sB + s * 16384;
-        tma_load_5d(st, &p.tmZ, &full[s], 0, 0, 0, 0, ti);           // re, classes 0..3
-        tma_load_5d(st + 4096, &p.tmZ, &full[s], 0, 1, 0, 0, ti);    // re, classes 4..7
-        tma_load_5d(st + 8192, &p.tmZ, &full[s], 0, 0, 0, 1, ti);    // im
-        tma_load_5d(st + 12288, &p.tmZ, &full[s], 0, 1, 0, 1, ti);
+        const int ta = (ti / p.ktiles) * p.kt_all + p.kt0 + ti % p.ktiles;   // tile index in the whole tensor
+        tma_load_5d(st, &p.tmZ, &full[s], 0, 0, 0, 0, ta);           // re, classes 0..3
+        tma_load_5d(st + 4096, &p.tmZ, &full[s], 0, 1, 0, 0, ta);    // re, classes 4..7
+        tma_load_5d(st + 8192, &p.tmZ, &full[s], 0, 0, 0, 1, ta);    // im
+        tma_load_5d(st + 12288, &p.tmZ, &full[s], 0, 1, 0, 1, ta);
       }
     }
     __syncwarp();
@@ -355,7 +357,8 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
     dft_partner_twiddles(tw, tp);
     int n = 0;
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, ++n) {
-      const int r = ti / p.ktiles, k0 = (ti - r * p.ktiles) * 8;
+      const int r = ti / p.ktiles, k0 = (p.kt0 + ti - r * p.ktiles) * 8;
+      const int ta = r * p.kt_all + p.kt0 + (ti - r * p.ktiles);   // tile index in the whole tensor
       const int ka = k0 + 2 * kpi;
       const int buf = n & 1, use = n >> 1;
       // per-row output factors:  out = x * sc + off(parity of the longitude)
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
         rsa = rs.x; rsb = rs.y;
       } else {
         // tiled latspec: element (m, plane, r, k) at ((tile * 2 + plane) * M2 + m / 8) * 64 + (m % 8) * 8 + k % 8, tile = r * ktiles + k / 8
-        const float* zt = p.Z + (size_t)ti * 2 * p.M2 * 64 + 2 * kpi;
+        const float* zt = p.Z + (size_t)ta * 2 * p.M2 * 64 + 2 * kpi;
         const float2 z0 = *reinterpret_cast<const float2*>(zt);
         z0a = z0.x; z0b = z0.y;
         if (p.has_nyq) {
@@ -439,7 +442,8 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   if (is_mma) tmem_dealloc(tmem, 512);
 }
 
-int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int mode, cudaStream_t st) {
+// k_begin / k_end: latitude range [k_begin, k_end) to produce (k_begin a multiple of 8; k_end < 0: all rows) -- the other rows of y are not touched
+int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int C, const float* bias, int mode, cudaStream_t st, int k_begin, int k_end) {
   const DftTables* t = static_cast<const DftTables*>(pl->dft_state);
   B200_REQUIRE(t != nullptr, "dft_synthesis: plan has no DFT tables");
   const int R = B * C;
@@ -448,7 +452,10 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   p.Z = Z; p.y = y; p.tw = t->tw; p.rowscale = pl->d_rowscale; p.bias = bias; p.trash = t->trash; p.prof = dft_prof_buffer();
   p.R = R; p.C = C; p.nlat = pl->nlat; p.nlon = pl->nlon; p.kp = pl->kp; p.mmax = pl->mmax;
   p.N2 = t->N2; p.half = t->half; p.qpr = t->qpr; p.nrep = t->nrep; p.mode = mode;
-  p.ktiles = pl->kp / 8; p.ntiles = R * p.ktiles;
+  if (k_end < 0 || k_end > pl->kp) k_end = pl->kp;
+  B200_REQUIRE(k_begin >= 0 && k_begin % 8 == 0 && k_begin < k_end, "dft_synthesis: bad latitude range [%d, %d)", k_begin, k_end);
+  p.kt_all = pl->kp / 8; p.kt0 = k_begin / 8;
+  p.ktiles = (k_end - k_begin + 7) / 8; p.ntiles = R * p.ktiles;
   p.has_nyq = (pl->mmax == pl->nlon / 2 + 1) ? 1 : 0;
   p.idesc = make_idesc(64, 0, 1, 0);
   p.M2 = t->M2;
@@ -471,7 +478,8 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   const int ctas = p.ntiles < sms ? p.ntiles : sms;
 #define B200_LAUNCH_SYN(TT, NN)                                                                                                          \
   do {                                                                                                                                  \
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_synthesis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    struct Tag {};                                                                                                                        \
+    B200_CHECK_CUDA((ensure_dynamic_smem<Tag>(dft_synthesis_kernel<TT, NN>, smem)));                                                     \
     dft_synthesis_kernel<TT, NN><<<ctas, kDftSynThreads, smem, st>>>(p);                                                                 \
   } while (0)
 #define B200_DISPATCH_SYN(TT)                                            \
@@ -850,7 +858,8 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   const int threads = 32 * (6 + (t->nkb == 3 ? 12 : 8));
 #define B200_LAUNCH_ANA(TT, NN)                                                                                                          \
   do {                                                                                                                                  \
-    B200_CHECK_CUDA(cudaFuncSetAttribute(dft_analysis_kernel<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    struct Tag {};                                                                                                                        \
+    B200_CHECK_CUDA((ensure_dynamic_smem<Tag>(dft_analysis_kernel<TT, NN>, smem)));                                                      \
     dft_analysis_kernel<TT, NN><<<ctas, threads, smem, st>>>(p);                                                                         \
   } while (0)
 #define B200_DISPATCH_ANA(TT)                                            \

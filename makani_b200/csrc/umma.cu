@@ -226,13 +226,14 @@ struct SynTraits {
     alignas(64) CUtensorMap tmA_lo, tmB_lo;   // residuals of the table and of spec (split mode)
     float* Z;
     int L, M, nlat, kp, C, cp, PB, nblk, N, m0;
+    int kc0, kc1;           // latitude range [kc0, kc1) of this launch (kc0 a multiple of 128): the tiles cover these rows only
     int tiled, M2, KT, B;   // tiled output for the tensor-core DFT (dft.cu): Z[r][k / 8][p][m / 8][m % 8][k % 8], orders padded to 8 * M2
     uint32_t idesc;
   };
   struct Tile { int m, k0, n0, lbeg; };
   __device__ static bool make_tile(const Params& p, Tile& t, int bx, int by, int bz) {
     t.m = bz;
-    t.k0 = 128 * bx;
+    t.k0 = p.kc0 + 128 * bx;
     t.n0 = p.N * by;
     t.lbeg = lstart(p.m0 + t.m);
     return true;
@@ -285,7 +286,7 @@ struct SynTraits {
       scratch[n] = o;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
-    const bool kok = k < p.kp;
+    const bool kok = k < p.kc1;
     const int kk = kok ? k : 0;
     float* zb = p.tiled ? p.Z + (size_t)(kk >> 3) * 2 * p.M2 * 64 + (t.m >> 3) * 64 + (t.m & 7) * 8 + (kk & 7)
                         : p.Z + (size_t)t.m * p.PB * p.C * p.kp + kk;
@@ -613,7 +614,7 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
   if (ntiles <= 0) return 0;
   const size_t smem = smem_bytes(p);
   if (smem > 232448) { set_error("umma: %zu bytes of shared memory needed", smem); return B200SHT_ERR_UNSUPPORTED; }
-  B200_CHECK_CUDA(cudaFuncSetAttribute(umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_CHECK_CUDA((ensure_dynamic_smem<T>(umma_kernel<T>, smem)));
   // static round-robin over tiles: an odd CTA count not divisible by 3 keeps tile-grid periods (2 l- or m-tiles, 3 or 6 n/k-tiles)
   // from locking heavy tiles onto the same CTAs
   const int sms = usable_sms(sm_count());
@@ -676,9 +677,14 @@ int legendre_analysis_umma(const Plan* pl, const float* X, float* spec, int B, i
   return launch<AnaTraits>(p, grid, st);
 }
 
-int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo) {
+// k_begin / k_end: latitude range [k_begin, k_end) to produce (k_begin a multiple of 128; k_end < 0: up to kp)
+int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, int C, int tiled, cudaStream_t st, const float* spec_lo, int k_begin,
+                            int k_end) {
   SynTraits::Params p;
   memset(&p, 0, sizeof(p));
+  if (k_end < 0 || k_end > pl->kp) k_end = pl->kp;
+  B200_REQUIRE(k_begin >= 0 && k_begin % 128 == 0 && k_begin < k_end, "legendre_synthesis: bad latitude range [%d, %d)", k_begin, k_end);
+  p.kc0 = k_begin; p.kc1 = k_end;
   const int cp = round_up(C, 4), PB = 2 * B, JP = PB * cp;
   p.Z = Z; p.L = pl->lmax; p.M = pl->mmax; p.nlat = pl->nlat; p.kp = pl->kp; p.C = C; p.cp = cp; p.PB = PB; p.m0 = pl->m0;
   p.tiled = tiled; p.M2 = (pl->mmax + 7) / 8; p.KT = pl->kp / 8; p.B = B;
@@ -713,7 +719,7 @@ int legendre_synthesis_umma(const Plan* pl, const float* spec, float* Z, int B, 
   pick_stages(&p, (16384 + 4096 * p.nblk) * (p.split ? 2 : 1), ceil_div(pl->lmax, 32));
   p.tx_bytes = (16384 + 4096 * p.nblk) * (p.split ? 2 : 1);
   set_accumulators(&p, p.N);
-  dim3 grid(ceil_div(pl->kp, 128), ceil_div(JP, p.N), tiled ? 8 * p.M2 : pl->mmax);
+  dim3 grid(ceil_div(k_end - k_begin, 128), ceil_div(JP, p.N), tiled ? 8 * p.M2 : pl->mmax);
   return launch<SynTraits>(p, grid, st);
 }
 

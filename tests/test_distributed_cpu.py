@@ -111,7 +111,7 @@ def _worker(rank, world, port, h, w, q):
         q.put((rank, None, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("h,w", [(2, 1), (1, 2), (2, 2)])
+@pytest.mark.parametrize("h,w", [(2, 1), (1, 2), (2, 2), (4, 2)])   # (4, 2): the grid of BASELINE configs[3] on 8 ranks, uneven splits in every dimension
 def test_distributed_sht_matches_serial_oracle(h, w):
     world = h * w
     ctx = mp.get_context("spawn")
