@@ -238,6 +238,9 @@ int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float
 /* wait-time profile of the tensor-core DFT kernels (environment B200SHT_DFT_PROF=1): 16 counters of SM clocks, accumulated over all launches since the
  * last call and cleared by it (slots: see csrc/dft.cu).  All zeros when the profile is off.  Synchronises the device. */
 int b200sht_debug_dft_profile(uint64_t* counters16);
+/* Programmatic dependent launch between the tcgen05 kernels of a call sequence (prologue of kernel i+1 under the tail of kernel i; environment
+ * B200SHT_PDL sets the initial value, default on).  Returns the previous setting.  Results do not depend on it. */
+int b200sht_debug_set_pdl(int on);
 /* Latitude chunks of the fused (longitude analysis -> Legendre analysis) pair inside b200sht_sht_forward / _inverse_adjoint and the
  * SpectralConv entry points at B200SHT_PREC_TF32: n > 1 forces n chunks, 1 switches chunking off, 0 restores the default (by size; the
  * environment variable B200SHT_LAT_CHUNKS sets the initial value).  Returns the previous setting.  Results are identical up to the

@@ -639,6 +639,22 @@ int b200sht_spectral_conv_forward_host(const b200sht_plan* f, const b200sht_plan
   return rc;
 }
 
+}  // extern "C"
+namespace b200sht {
+static int& pdl_flag() {
+  static int on = [] { const char* e = getenv("B200SHT_PDL"); return e ? atoi(e) : 1; }();
+  return on;
+}
+bool pdl_enabled() { return pdl_flag() != 0; }
+}  // namespace b200sht
+extern "C" {
+
+int b200sht_debug_set_pdl(int on) {
+  const int old = b200sht::pdl_flag();
+  b200sht::pdl_flag() = on;
+  return old;
+}
+
 int b200sht_debug_set_lat_chunks(int n) {
   const int old = lat_chunks_forced();
   lat_chunks_forced() = n;

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 #include "../../include/b200sht.h"
 
 #define HD __host__ __device__ __forceinline__
@@ -97,6 +98,28 @@ inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes) {
   if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = (int)bytes;
   return e;
 }
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------------
+// The hot kernels call pdl_trigger() first thing (their successor in the stream may be scheduled as soon as every CTA of this grid has done
+// so or exited) and pdl_wait() after their prologue (barrier init, TMEM allocation, tensor-map prefetch, resident constant tables), i.e.
+// before the first access to memory another kernel produces or still reads: the wait returns once all prerequisite grids have COMPLETED and
+// their writes are visible.  A successor launched with launch_pdl() therefore overlaps its launch latency and prologue with the tail of this
+// kernel; launched normally it serialises as always.  Both instructions are no-ops without a programmatic dependency.
+// Rule for every kernel launched through launch_pdl(): no global load / store / TMA of non-constant data before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // B200SHT_PDL (default: see capi.cu)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int usable_sms(int sms) { const int r = sm_reserve(); return (r > 0 && sms - r >= 1) ? sms - r : sms; }
 
 }  // namespace b200sht

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  pdl_trigger();
   const int quad = warp & 3, sub = warp >> 2;
   const int subs = 4 / p.nrep;                                  // k pairs per replica
   const bool is_tma = (warp == 15), is_mma = (warp == 11);
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(kDftSynThreads, 1) dft_synthesis_kernel(const 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const long long t_cta0 = (kDftProfile && p.prof && threadIdx.x == 0) ? clock64() : 0;
+  pdl_wait();   // the prologue read plan constants only (twiddles); the latspec tiles, bias and y belong to other kernels until here
 
   if (is_tma) {
     if (lane == 0) {
@@ -480,7 +482,7 @@ int dft_synthesis(const Plan* pl, const float* Z, void* y, int dtype, int B, int
   do {                                                                                                                                  \
     struct Tag {};                                                                                                                        \
     B200_CHECK_CUDA((ensure_dynamic_smem<Tag>(dft_synthesis_kernel<TT, NN>, smem)));                                                     \
-    dft_synthesis_kernel<TT, NN><<<ctas, kDftSynThreads, smem, st>>>(p);                                                                 \
+    B200_CHECK_CUDA(launch_pdl(dft_synthesis_kernel<TT, NN>, dim3(ctas), dim3(kDftSynThreads), smem, st, p));                                                                 \
   } while (0)
 #define B200_DISPATCH_SYN(TT)                                            \
   switch (t->N2) {                                                       \
@@ -501,6 +503,12 @@ __host__ __device__ constexpr int dft_box_group(int N2, int es) { return (N2 * e
 
 // 3-D view of the samples for the analysis loader: (column inside a group of gs row segments, group, row), box (box_cols, 8 / gs, 16), no swizzle
 static int make_tmap_segments(CUtensorMap* tm, const void* base, bool bf16, int nlon, int gs, long long rows, int box_cols) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = 3; key.kind = bf16 ? 5 : 4;
+  key.dims[0] = nlon; key.dims[1] = gs; key.dims[2] = rows; key.box[0] = box_cols;
+  int slot = 0;
+  if (tmap_lookup(key, tm, &slot)) return 0;
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
   static thread_local bool ctx_bound = false;
@@ -516,6 +524,7 @@ static int make_tmap_segments(CUtensorMap* tm, const void* base, bool bf16, int 
   CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gd, gst, bx, el,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (segments) failed (%d)", (int)r); return B200SHT_ERR_CUDA; }
+  tmap_store(key, tm, slot);
   return 0;
 }
 
@@ -574,6 +583,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  pdl_trigger();
   const int nkb = p.nkb;
   const int N2 = N2T > 0 ? N2T : p.N2;
   // row segments per sample box group: the smallest gs with (gs * N2 elements) a multiple of 16 bytes, so that the segments gm, gm + gs, ...
@@ -610,6 +620,7 @@ __global__ void __launch_bounds__(576, 1) dft_analysis_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const long long t_cta0 = (kDftProfile && p.prof && threadIdx.x == 0) ? clock64() : 0;
+  pdl_wait();   // the prologue read plan constants only (twiddles); samples and latspec belong to other kernels until here
 
   if (warp == 4) {
     if (lane == 0) {
@@ -860,7 +871,7 @@ int dft_analysis(const Plan* pl, const void* x, int dtype, int B, int C, float* 
   do {                                                                                                                                  \
     struct Tag {};                                                                                                                        \
     B200_CHECK_CUDA((ensure_dynamic_smem<Tag>(dft_analysis_kernel<TT, NN>, smem)));                                                      \
-    dft_analysis_kernel<TT, NN><<<ctas, threads, smem, st>>>(p);                                                                         \
+    B200_CHECK_CUDA(launch_pdl(dft_analysis_kernel<TT, NN>, dim3(ctas), dim3(threads), smem, st, p));                                                                         \
   } while (0)
 #define B200_DISPATCH_ANA(TT)                                            \
   switch (t->N2) {                                                       \

@@ -26,6 +26,8 @@ constexpr int kWpO = 128, kWpL = 32;
 __global__ void __launch_bounds__(256) weight_pack_dhconv_kernel(float2* __restrict__ wn, float* __restrict__ wp, int L, int GC /*G*Cig*/, int Cog,
                                                                  int cop, int to_native, int rnd) {
   __shared__ float2 tile[kWpO][kWpL + 1];
+  pdl_trigger();
+  pdl_wait();   // the weight (optimizer) and the packed buffer (the previous step's mix kernels may still read its memory) belong to earlier kernels
   const int gi = blockIdx.z;
   const int o0 = blockIdx.y * kWpO, l0 = blockIdx.x * kWpL;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -94,7 +96,8 @@ int mix_weight_relayout(int op, const void* w_native, float* w_packed, int L, in
   if (op == B200SHT_OP_DHCONV) {
     dim3 grid(ceil_div(L, kWpL), ceil_div(cop, kWpO), G * Cig);
     B200_REQUIRE(grid.z <= 65535, "mix_weight: G*Cig=%u exceeds grid limit", grid.z);
-    weight_pack_dhconv_kernel<<<grid, 256, 0, st>>>(static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop, to_native, round_tf32);
+    B200_CHECK_CUDA(launch_pdl(weight_pack_dhconv_kernel, grid, dim3(256), 0, st, static_cast<float2*>(const_cast<void*>(w_native)), w_packed, L, G * Cig, Cog, cop,
+                               to_native, round_tf32));
   } else if (op == B200SHT_OP_SHARED || op == B200SHT_OP_LDEP) {
     B200_REQUIRE(G == 1, "mix_weight: OP_SHARED/OP_LDEP are ungrouped");
     const long long rows = (op == B200SHT_OP_SHARED) ? Ci : (long long)L * Ci;

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
   int* epi_scratch = reinterpret_cast<int*>(tmem_slot + 4);   // 2 x kEpiScratch ints, double-buffered by tile parity (epilogue warps only)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
+  pdl_trigger();   // the next kernel of the stream may be scheduled while this one runs (it waits for our completion before touching data)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_kernel(const __grid_cons
   const uint32_t tmem = *tmem_slot;
   const int ntiles = p.gx * p.gy * p.gz;
   const int nbuf = p.nbuf;
+  pdl_wait();      // prologue done (barriers, TMEM, tensor-map prefetch): from here on this kernel reads what its predecessors wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -620,7 +622,7 @@ static int launch(typename T::Params& p, dim3 grid, cudaStream_t st) {
   const int sms = usable_sms(sm_count());
   int ctas = (int)(ntiles < sms ? ntiles : sms);
   while (ctas > 1 && (ctas % 2 == 0 || ctas % 3 == 0)) --ctas;
-  umma_kernel<T><<<ctas, kUmmaThreads, smem, st>>>(p);
+  B200_CHECK_CUDA(launch_pdl(umma_kernel<T>, dim3(ctas), dim3(kUmmaThreads), smem, st, p));
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstring>
 
 namespace b200sht {
 
@@ -211,9 +212,52 @@ inline PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Encoded tensor maps are a pure function of (base, shape, strides, box, swizzle): in steady state the caching allocator hands the same
+// buffers to every step, so the 2-3 driver encodes per launch are replaced by a lookup in a small per-thread direct-mapped cache.
+struct TmapKey {
+  const void* base;
+  long long dims[5], strides[5];
+  int box[5];
+  int rank, kind;   // kind: 0 fp32 / 128-byte swizzle, 1 same with 32-byte atoms (MN-major), 2 fp32 rows, 3 bf16 rows, 4 fp32 segments, 5 bf16 segments
+};
+struct TmapCache {
+  static constexpr int kSlots = 128;
+  CUtensorMap maps[kSlots];
+  TmapKey keys[kSlots];
+  bool used[kSlots];
+};
+inline TmapCache& tmap_cache() {
+  static thread_local TmapCache* c = [] { TmapCache* p = new TmapCache(); memset(p->used, 0, sizeof(p->used)); return p; }();
+  return *c;
+}
+inline int tmap_slot(const TmapKey& k) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof(TmapKey); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return (int)(h % TmapCache::kSlots);
+}
+inline bool tmap_lookup(const TmapKey& k, CUtensorMap* tm, int* slot) {
+  TmapCache& c = tmap_cache();
+  *slot = tmap_slot(k);
+  if (c.used[*slot] && memcmp(&c.keys[*slot], &k, sizeof(TmapKey)) == 0) { memcpy(tm, &c.maps[*slot], sizeof(CUtensorMap)); return true; }
+  return false;
+}
+inline void tmap_store(const TmapKey& k, const CUtensorMap* tm, int slot) {
+  TmapCache& c = tmap_cache();
+  memcpy(&c.maps[slot], tm, sizeof(CUtensorMap));
+  c.keys[slot] = k;
+  c.used[slot] = true;
+}
+
 // fp32 tensor map, 128-byte swizzle.  dims[0] is the contiguous dimension; strides (in floats) for dims 1..rank-1.
 // mn_major: the operand is read M/N-major by kind::tf32, which needs the 128-byte swizzle with 32-byte atoms
 inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides, const int* box, bool mn_major = false) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.kind = mn_major ? 1 : 0;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.strides[i] = i ? strides[i] : 1; key.box[i] = box[i]; }
+  int slot = 0;
+  if (tmap_lookup(key, tm, &slot)) return 0;
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return B200SHT_ERR_UNSUPPORTED; }
   // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context.  A thread that has made no runtime call yet (PyTorch's autograd
@@ -232,6 +276,7 @@ inline int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank); return B200SHT_ERR_CUDA; }
+  tmap_store(key, tm, slot);
   return 0;
 }
 
