@@ -551,7 +551,7 @@ def run_gpu_arm(args):
                 torch.cuda.synchronize()
         ms_dev = timed(dp_step, args.steps, args.warmup)
         host_ms = host_enqueue.get("ms_per_step")
-        # opt-in (round-2 experiment, not part of the default line): the same step replayed from a CUDA graph, reported separately
+        # the same step replayed from a CUDA graph, reported separately (`value` stays the eager step: it is what N > 1 and e2e run)
         if args.graph and world == 1:
             graph_info = try_cuda_graph()
         if sampler:
@@ -881,7 +881,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stages", action="store_true", help="skip per-stage kernel timing")
     ap.add_argument("--no-hxw", action="store_true", help="N > 1: skip the additional h x w spatial-model-parallel measurement of the same block")
-    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph (opt-in experiment, N = 1)")
+    ap.add_argument("--graph", action="store_true", default=True, help="also time the step replayed from a CUDA graph (N = 1; reported as cuda_graph_replay, never as `value`)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
