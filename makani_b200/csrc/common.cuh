@@ -115,7 +115,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  // not while SMs are reserved for a collective on another stream (b200sht_spectral_conv_backward_ex): an early-launched successor would park its
+  // CTAs on exactly the SMs that were left free for the NCCL kernel
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && sm_reserve() == 0) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
