@@ -355,13 +355,16 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dp_group = None
+    dp_mode = args.dp_mode
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # the gradient all-reduce runs beside two persistent kernels that leave it B200SHT_OVERLAP_SMS (8) SMs: a communicator of its own,
         # capped at as many CTAs, so that it starts at once instead of waiting for a kernel boundary
         try:
+            if dp_mode != "overlap":
+                raise RuntimeError("dp-mode trailing: default communicator")
             opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = int(os.environ.get("B200SHT_OVERLAP_SMS", "8")) or 8
+            opts.config.max_ctas = int(os.environ.get("B200SHT_DP_MAXCTAS", os.environ.get("B200SHT_OVERLAP_SMS", "8"))) or 8
             opts.config.min_ctas = 1
             dp_group = dist.new_group(list(range(world)), pg_options=opts)
         except Exception as e:   # older torch / NCCL: default communicator
@@ -498,13 +501,15 @@ def run_gpu_arm(args):
 
     # data parallel: the weight-gradient all-reduce is launched on a side stream as soon as the gradient is final (event recorded inside
     # b200sht_spectral_conv_backward_ex, before the two input-gradient stages), so it overlaps legendre_synthesis + fft_synthesis
-    side = torch.cuda.Stream(dev) if world > 1 else None
-    if world > 1:
+    side = torch.cuda.Stream(dev) if (world > 1 and dp_mode == "overlap") else None
+    if world > 1 and dp_mode == "overlap":
         conv.wgrad_ready_event = torch.cuda.Event()
 
     def dp_step():
         step(x_dev)
-        if world > 1:
+        if world > 1 and dp_mode != "overlap":   # the all-reduce trails the backward pass on the compute stream (default communicator)
+            dist.all_reduce(torch.view_as_real(conv.weight.grad))
+        elif world > 1:
             side.wait_event(conv.wgrad_ready_event)
             with torch.cuda.stream(side):
                 dist.all_reduce(torch.view_as_real(conv.weight.grad), group=dp_group)
@@ -684,7 +689,7 @@ def run_gpu_arm(args):
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if precision == "tf32" else ("f32 (3 x tf32 Legendre)" if precision == "fp32x3" else "f32"),
         "data": "synthetic",
         "config": {"workload": wl, "shape": [1, C, nlat_i, nlon_i], "activations": args.act, "contraction": {"tf32": "tcgen05 kind::tf32, fp32 accumulate", "fp32x3": "Legendre: 3 x TF32 on tcgen05 (fp32 operands); mix, FFT: fp32 FMA"}.get(precision, "fp32 FMA (CUDA cores)"),
-                   "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "operator": "dhconv", "lmax": L, "mmax": M,
+                   "batch_per_gpu": 1, "global_batch": world, "parallelism": f"dp{world}" if world > 1 else "single", "dp_allreduce": dp_mode if world > 1 else None, "operator": "dhconv", "lmax": L, "mmax": M,
                    "l2": f"256 MiB buffer written between timed iterations (L2 flush); input {x_host.numel() * x_host.element_size() / 1e6:.0f} MB",
                    "weight_relayout_in_step": True, "flops_fwd_bwd_nnz": flops_fwd_bwd(wl)},
         "clocks": clocks,
@@ -883,6 +888,8 @@ def main():
     ap.add_argument("--no-hxw", action="store_true", help="N > 1: skip the additional h x w spatial-model-parallel measurement of the same block")
     ap.add_argument("--graph", action="store_true", default=True, help="also time the step replayed from a CUDA graph (N = 1; reported as cuda_graph_replay, never as `value`)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--dp-mode", default=os.environ.get("B200SHT_DP_MODE", "overlap"), choices=["overlap", "trailing"],
+                    help="N > 1: weight-gradient all-reduce on a side stream behind the wgrad event (overlap) or after the backward pass on the compute stream (trailing)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
