@@ -888,8 +888,9 @@ def main():
     ap.add_argument("--no-hxw", action="store_true", help="N > 1: skip the additional h x w spatial-model-parallel measurement of the same block")
     ap.add_argument("--graph", action="store_true", default=True, help="also time the step replayed from a CUDA graph (N = 1; reported as cuda_graph_replay, never as `value`)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
-    ap.add_argument("--dp-mode", default=os.environ.get("B200SHT_DP_MODE", "overlap"), choices=["overlap", "trailing"],
-                    help="N > 1: weight-gradient all-reduce on a side stream behind the wgrad event (overlap) or after the backward pass on the compute stream (trailing)")
+    ap.add_argument("--dp-mode", default=os.environ.get("B200SHT_DP_MODE", "trailing"), choices=["overlap", "trailing"],
+                    help="N > 1: weight-gradient all-reduce after the backward pass on the compute stream (trailing, default: measured faster, DESIGN.md section 7) or on a "
+                         "side stream behind the wgrad event with reserved SMs (overlap)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
