@@ -238,6 +238,22 @@ int b200sht_debug_dft_host(int N, int mmax, int direction, int scale_mode, float
 /* wait-time profile of the tensor-core DFT kernels (environment B200SHT_DFT_PROF=1): 16 counters of SM clocks, accumulated over all launches since the
  * last call and cleared by it (slots: see csrc/dft.cu).  All zeros when the profile is off.  Synchronises the device. */
 int b200sht_debug_dft_profile(uint64_t* counters16);
+/* ------------------------------------------------------------------ pointwise tail of the SFNO block */
+/* Replaces torch.nn.InstanceNorm2d(num_features, eps, affine) (+ the nn.GELU that follows it) as built at makani/models/networks/sfnonet.py:618-620 and
+ * applied at :385-406, and the bias + GELU of the 1x1-convolution stacks (makani/models/common/layers.py:537-760).  x, y, dy, dx: [B][C][hw] contiguous, float or
+ * bf16 (dtype); gamma / beta / bias: float [C] (null: 1 / 0); stats: float [B*C][2] (mean, rstd), written by forward, read by backward; sums: float [B*C][2]
+ * written by backward: per row sum g and sum g * xhat -- dbeta[c] / dgamma[c] are their sums over the batch; workspace: b200sht_pointwise_workspace_floats floats.
+ * gelu != 0 fuses y = gelu(norm(x)) (exact erf GELU).  Statistics are biased (1 / hw), as InstanceNorm uses them. */
+int64_t b200sht_pointwise_workspace_floats(int B, int C, int64_t hw);
+int b200sht_instance_norm_forward(const void* x, void* y, const float* gamma, const float* beta, float* stats, float* workspace, int dtype, int B, int C,
+                                  int64_t hw, float eps, int gelu, void* stream);
+int b200sht_instance_norm_backward(const void* x, const void* dy, void* dx, const float* gamma, const float* beta, const float* stats, float* sums,
+                                   float* workspace, int dtype, int B, int C, int64_t hw, int gelu, void* stream);
+/* y = gelu(x + bias[c]);  dx = dy * gelu'(x + bias[c]), row_sums: float [B*C][2] with sum dx in [.][0] (dbias[c] = its sum over the batch; may be null) */
+int b200sht_bias_gelu_forward(const void* x, const float* bias, void* y, int dtype, int B, int C, int64_t hw, void* stream);
+int b200sht_bias_gelu_backward(const void* x, const float* bias, const void* dy, void* dx, float* row_sums, float* workspace, int dtype, int B, int C, int64_t hw,
+                               void* stream);
+
 /* Programmatic dependent launch between the tcgen05 kernels of a call sequence (prologue of kernel i+1 under the tail of kernel i; environment
  * B200SHT_PDL sets the initial value, default on).  Returns the previous setting.  Results do not depend on it. */
 int b200sht_debug_set_pdl(int on);

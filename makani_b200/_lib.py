@@ -71,6 +71,12 @@ _SIGNATURES = {
     "b200sht_spectral_conv_backward_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200sht_bias_grad": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "b200sht_spectral_conv_forward_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    # pointwise tail of the SFNO block (row N2)
+    "b200sht_pointwise_workspace_floats": (c_int64, [c_int, c_int, c_int64]),
+    "b200sht_instance_norm_forward": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_float, c_int, _P]),
+    "b200sht_instance_norm_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
+    "b200sht_bias_gelu_forward": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int64, _P]),
+    "b200sht_bias_gelu_backward": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P]),
     # debug / CPU-testable entry points (same device code compiled for the host)
     "b200sht_debug_fft_host": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "b200sht_debug_dft_host": (c_int, [c_int, c_int, c_int, c_int, c_float, _P, _P]),

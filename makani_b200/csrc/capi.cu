@@ -57,6 +57,15 @@ int mix_forward_umma(const Plan* pl, int op, const float* x, const void* w, cons
 int mix_backward_umma(const Plan* pl, int op, const float* x, const void* w, const float* gy, float* gx, void* gw, void* gcbias, int B, int G,
                       int Ci, int Co, cudaStream_t st);
 
+// pointwise tail of the SFNO block (norm.cu)
+int norm_splits(int rows, long long n);
+int instance_norm_forward(const void* x, void* y, const float* gamma, const float* beta, float* stats, float* ws, int dtype, int B, int C, long long hw, float eps,
+                          int gelu, cudaStream_t st);
+int instance_norm_backward(const void* x, const void* dy, void* dx, const float* gamma, const float* beta, const float* stats, float* sums, float* ws, int dtype,
+                           int B, int C, long long hw, int gelu, cudaStream_t st);
+int bias_gelu_forward(const void* x, const float* bias, void* y, int dtype, int B, int C, long long hw, cudaStream_t st);
+int bias_gelu_backward(const void* x, const float* bias, const void* dy, void* dx, float* row_sums, float* ws, int dtype, int B, int C, long long hw, cudaStream_t st);
+
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 static inline int cp_of(int C) { return round_up(C, 4); }
 // dims-only plan for the entry points that depend on (L, M) alone
@@ -648,6 +657,43 @@ static int& pdl_flag() {
 bool pdl_enabled() { return pdl_flag() != 0; }
 }  // namespace b200sht
 extern "C" {
+
+// ------------------------------------------------------------------------------ pointwise tail of the SFNO block (row N2)
+int64_t b200sht_pointwise_workspace_floats(int B, int C, int64_t hw) {
+  if (B <= 0 || C <= 0 || hw <= 0) return -1;
+  return (int64_t)B * C * norm_splits(B * C, hw) * 2;
+}
+static int check_pointwise(const void* a, const void* b, int dtype, const char* who) {
+  B200_REQUIRE(a && b, "%s: null argument", who);
+  B200_REQUIRE(dtype == B200SHT_F32 || dtype == B200SHT_BF16, "%s: unknown dtype %d", who, dtype);
+  return 0;
+}
+int b200sht_instance_norm_forward(const void* x, void* y, const float* gamma, const float* beta, float* stats, float* workspace, int dtype, int B, int C,
+                                  int64_t hw, float eps, int gelu, void* stream) {
+  int rc = check_pointwise(x, y, dtype, "instance_norm_forward");
+  if (rc) return rc;
+  B200_REQUIRE(stats && workspace, "instance_norm_forward: null stats / workspace");
+  return instance_norm_forward(x, y, gamma, beta, stats, workspace, dtype, B, C, hw, eps, gelu, S(stream));
+}
+int b200sht_instance_norm_backward(const void* x, const void* dy, void* dx, const float* gamma, const float* beta, const float* stats, float* sums,
+                                   float* workspace, int dtype, int B, int C, int64_t hw, int gelu, void* stream) {
+  int rc = check_pointwise(x, dy, dtype, "instance_norm_backward");
+  if (rc) return rc;
+  B200_REQUIRE(dx && stats && sums && workspace, "instance_norm_backward: null argument");
+  return instance_norm_backward(x, dy, dx, gamma, beta, stats, sums, workspace, dtype, B, C, hw, gelu, S(stream));
+}
+int b200sht_bias_gelu_forward(const void* x, const float* bias, void* y, int dtype, int B, int C, int64_t hw, void* stream) {
+  int rc = check_pointwise(x, y, dtype, "bias_gelu_forward");
+  if (rc) return rc;
+  return bias_gelu_forward(x, bias, y, dtype, B, C, hw, S(stream));
+}
+int b200sht_bias_gelu_backward(const void* x, const float* bias, const void* dy, void* dx, float* row_sums, float* workspace, int dtype, int B, int C, int64_t hw,
+                               void* stream) {
+  int rc = check_pointwise(x, dy, dtype, "bias_gelu_backward");
+  if (rc) return rc;
+  B200_REQUIRE(dx && workspace, "bias_gelu_backward: null argument");
+  return bias_gelu_backward(x, bias, dy, dx, row_sums, workspace, dtype, B, C, hw, S(stream));
+}
 
 int b200sht_debug_set_pdl(int on) {
   const int old = b200sht::pdl_flag();

@@ -25,6 +25,50 @@ def _tag_spatial(p):
     return p
 
 
+class Conv1x1(nn.Conv2d):
+    """`nn.Conv2d(cin, cout, 1)` with the reference's parameter names / shapes / init (weight [cout, cin, 1, 1], bias [cout]) whose forward is the
+    plain GEMM `W [cout, cin] @ x [B, cin, H*W]` on the NCHW tensor itself.  cuDNN runs a bf16 1x1 convolution as an NHWC implicit GEMM between two
+    layout conversions of the whole activation (profile of the sfno_sc3_layers8_edim384 step: 66 `nchwToNhwc` / `nhwcToNchw` launches, 11.5 ms of a
+    77 ms step); the longitude transforms on either side need NCHW, so the GEMM is done in that layout (cuBLAS, a library GEMM) and the conversions
+    disappear.  Same arithmetic (bf16 operands under autocast, fp32 accumulation), same gradients."""
+
+    def is_plain(self, x):
+        return self.groups == 1 and x.dim() == 4 and self.kernel_size == (1, 1) and self.padding_mode == "zeros"
+
+    def gemm(self, x):
+        """W @ x without the bias (the caller adds it, or fuses it with the activation that follows: `_run_stack`)"""
+        B, C, H, W = x.shape
+        return torch.matmul(self.weight.view(self.out_channels, self.in_channels), x.reshape(B, C, H * W)).view(B, self.out_channels, H, W)
+
+    def forward(self, x):
+        if not self.is_plain(x):
+            return super().forward(x)
+        y = self.gemm(x)
+        if self.bias is not None:
+            y = y + self.bias.to(y.dtype).view(1, -1, 1, 1)
+        return y
+
+
+def _run_stack(mods, x):
+    """nn.Sequential of 1x1 convolutions, activations and dropouts, with `conv -> (+ bias) -> GELU` as GEMM + one fused bias + GELU kernel
+    (makani_b200.norm.bias_gelu) where the pattern and the device allow it; otherwise module by module."""
+    from .norm import bias_gelu, fused_pointwise_enabled
+
+    mods = list(mods)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if (isinstance(m, Conv1x1) and isinstance(nxt, nn.GELU) and getattr(nxt, "approximate", "none") == "none" and x.is_cuda and fused_pointwise_enabled()
+                and m.is_plain(x)):
+            x = bias_gelu(m.gemm(x), m.bias)
+            i += 2
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
 class DropPath(nn.Module):
     """stochastic depth per sample (layers.py:49-90)"""
 
@@ -49,18 +93,18 @@ class EncoderDecoder(nn.Module):
             raise NotImplementedError(f"Error, input format {input_format} not supported.")
         mods, cur = [], input_dim
         for _ in range(num_layers):
-            conv = nn.Conv2d(cur, hidden_dim, 1, bias=True, groups=groups)
+            conv = Conv1x1(cur, hidden_dim, 1, bias=True, groups=groups)
             nn.init.normal_(_tag_spatial(conv.weight), mean=0.0, std=math.sqrt(2.0 / (cur // groups)))
             nn.init.constant_(_tag_spatial(conv.bias), 0.0)
             mods += [conv, act_layer()]
             cur = hidden_dim
-        out = nn.Conv2d(cur, output_dim, 1, bias=False, groups=groups)
+        out = Conv1x1(cur, output_dim, 1, bias=False, groups=groups)
         nn.init.normal_(_tag_spatial(out.weight), mean=0.0, std=math.sqrt(gain / (cur // groups)))
         mods.append(out)
         self.fwd = nn.Sequential(*mods)
 
     def forward(self, x):
-        return self.fwd(x)
+        return _run_stack(self.fwd, x)
 
 
 class MLP(nn.Module):
@@ -71,8 +115,8 @@ class MLP(nn.Module):
         super().__init__()
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
-        fc1 = nn.Conv2d(in_features, hidden_features, 1, bias=True)
-        fc2 = nn.Conv2d(hidden_features, out_features, 1, bias=output_bias)
+        fc1 = Conv1x1(in_features, hidden_features, 1, bias=True)
+        fc2 = Conv1x1(hidden_features, out_features, 1, bias=output_bias)
         nn.init.normal_(_tag_spatial(fc1.weight), mean=0.0, std=math.sqrt(2.0 / in_features))
         nn.init.constant_(_tag_spatial(fc1.bias), 0.0)
         nn.init.normal_(_tag_spatial(fc2.weight), mean=0.0, std=math.sqrt(gain / hidden_features))
@@ -87,7 +131,7 @@ class MLP(nn.Module):
         self.fwd = nn.Sequential(fc1, act_layer(), drop, fc2, drop)
 
     def forward(self, x):
-        return self.fwd(x)
+        return _run_stack(self.fwd, x)
 
 
 class _Backend:
@@ -151,7 +195,7 @@ class NeuralOperatorBlock(nn.Module):
     def _make_skip(self, name, kind, embed_dim, gain):
         """'linear': 1x1 conv initialised with half the variance budget; 'identity'; 'none' (no attribute at all, as the reference)."""
         if kind == "linear":
-            conv = nn.Conv2d(embed_dim, embed_dim, 1, 1, bias=False)
+            conv = Conv1x1(embed_dim, embed_dim, 1, 1, bias=False)
             gain /= 2.0
             nn.init.normal_(conv.weight, std=math.sqrt(gain / embed_dim))
             setattr(self, name, conv)
@@ -163,11 +207,17 @@ class NeuralOperatorBlock(nn.Module):
         return gain
 
     def forward(self, x):
+        from .norm import InstanceNorm2d as FusedInstanceNorm2d
+
         x, residual = self.filter(x)
-        x = self.norm0(x)
-        if hasattr(self, "inner_skip"):
-            x = x + self.inner_skip(residual)
-        x = self.act_layer0(x)
+        if (isinstance(self.norm0, FusedInstanceNorm2d) and not hasattr(self, "inner_skip") and isinstance(self.act_layer0, nn.GELU)
+                and getattr(self.act_layer0, "approximate", "none") == "none"):
+            x = self.norm0(x, gelu=True)     # norm0 -> GELU in one pass (sfnonet.py:387-392 with inner_skip "none")
+        else:
+            x = self.norm0(x)
+            if hasattr(self, "inner_skip"):
+                x = x + self.inner_skip(residual)
+            x = self.act_layer0(x)
         if hasattr(self, "mlp"):
             x = self.mlp(x)
         x = self.drop_path(self.norm1(x))
@@ -204,7 +254,9 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         dpr = [v.item() for v in torch.linspace(0, path_drop_rate, num_layers)]
 
         if normalization_layer == "instance_norm":
-            norm = partial(nn.InstanceNorm2d, num_features=embed_dim, eps=1e-6, affine=True, track_running_stats=False)
+            from .norm import InstanceNorm2d as FusedInstanceNorm2d   # nn.InstanceNorm2d subclass: same parameters / state dict, CUDA kernels of csrc/norm.cu
+
+            norm = partial(FusedInstanceNorm2d, num_features=embed_dim, eps=1e-6, affine=True, track_running_stats=False)
         elif normalization_layer == "none":
             norm = nn.Identity
         else:
@@ -223,7 +275,7 @@ class SphericalFourierNeuralOperatorNet(nn.Module):
         self.decoder = EncoderDecoder(num_layers=encoder_layers, input_dim=embed_dim, output_dim=out_chans, hidden_dim=int(decoder_ratio * embed_dim),
                                       act_layer=act, gain=0.5 if big_skip else 1.0, input_format="nchw")
         if big_skip:
-            self.residual_transform = nn.Conv2d(inp_chans, out_chans, 1, bias=False)
+            self.residual_transform = Conv1x1(inp_chans, out_chans, 1, bias=False)
             self.residual_transform.weight.is_shared_mp = ["spatial"]
             self.residual_transform.weight.sharded_dims_mp = [None, None, None, None]
             nn.init.normal_(self.residual_transform.weight, mean=0.0, std=math.sqrt(0.5 / inp_chans))

@@ -10,7 +10,7 @@ from makani_b200.sfno import SphericalFourierNeuralOperatorNet
 dev = torch.device("cuda", 0)
 cfg = MODEL_WORKLOADS["sfno_sc3_layers8_edim384"]
 torch.manual_seed(333)
-net = SphericalFourierNeuralOperatorNet(**cfg).to(dev)
+net = SphericalFourierNeuralOperatorNet(**cfg, precision="tf32").to(dev)   # the mode bench.py times (allow_tf32, as makani/train.py:87)
 x = torch.randn(1, cfg["inp_chans"], *cfg["inp_shape"], device=dev)
 
 
