@@ -38,7 +38,12 @@ class Conv1x1(nn.Conv2d):
     def gemm(self, x):
         """W @ x without the bias (the caller adds it, or fuses it with the activation that follows: `_run_stack`)"""
         B, C, H, W = x.shape
-        return torch.matmul(self.weight.view(self.out_channels, self.in_channels), x.reshape(B, C, H * W)).view(B, self.out_channels, H, W)
+        w = self.weight.view(1, self.out_channels, self.in_channels)
+        if w.dtype != x.dtype and x.dtype in (torch.bfloat16, torch.float16):
+            w = w.to(x.dtype)            # activations already in the autocast dtype: cast the (small) weight once, before the batch expansion
+        # bmm on (B, cout, cin) x (B, cin, H*W): the output is the contiguous NCHW tensor.  (torch.matmul(2-D, 3-D) folds the batch into the rows of the
+        # TRANSPOSED problem and hands back a transposed view: the copy that makes it contiguous cost 50 ms per model step when this was first measured.)
+        return torch.bmm(w.expand(B, -1, -1), x.reshape(B, C, H * W)).view(B, self.out_channels, H, W)
 
     def forward(self, x):
         if not self.is_plain(x):
