@@ -126,7 +126,29 @@ __global__ void __launch_bounds__(kNormThreads) norm_kernel(const NormArgs a) {
   constexpr bool kNeedDy = (MODE == 2 || MODE == 3 || MODE == 5), kWrites = (MODE == 1 || MODE == 3 || MODE == 4 || MODE == 5);
   if (VEC) {
     constexpr int kN = Pack<T>::kN;
-    for (long long i = beg + (long long)threadIdx.x * kN; i < end; i += (long long)kNormThreads * kN) {   // beg, n multiples of kN: whole packets
+    constexpr long long kStride = (long long)kNormThreads * kN;
+    long long i = beg + (long long)threadIdx.x * kN;   // beg, n multiples of kN: whole packets
+    // two packets per tensor in flight per thread (first measurement of the one-packet loop: 45-50 % of HBM, latency bound at 5 CTAs per SM)
+    for (; i + kStride < end; i += 2 * kStride) {
+      Pack<T> px0, px1, pd0, pd1, po0, po1;
+      px0.load(x + i);
+      px1.load(x + i + kStride);
+      if (kNeedDy) { pd0.load(dy + i); pd1.load(dy + i + kStride); }
+#pragma unroll
+      for (int j = 0; j < kN; ++j) {
+        float ov = 0.f;
+        element(px0.get(j), kNeedDy ? pd0.get(j) : 0.f, ov);
+        if (kWrites) po0.set(j, ov);
+      }
+#pragma unroll
+      for (int j = 0; j < kN; ++j) {
+        float ov = 0.f;
+        element(px1.get(j), kNeedDy ? pd1.get(j) : 0.f, ov);
+        if (kWrites) po1.set(j, ov);
+      }
+      if (kWrites) { po0.store(out + i); po1.store(out + i + kStride); }
+    }
+    for (; i < end; i += kStride) {
       Pack<T> px, pd, po;
       px.load(x + i);
       if (kNeedDy) pd.load(dy + i);
@@ -175,7 +197,7 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, float* _
 }
 
 int norm_splits(int rows, long long n) {
-  long long s = (4LL * 148 + rows - 1) / rows;          // >= 4 CTAs per SM in flight
+  long long s = (8LL * 148 + rows - 1) / rows;          // >= 8 CTAs per SM's worth of blocks
   const long long by_len = n / 2048 > 0 ? n / 2048 : 1;  // but not less than 2048 elements per CTA
   if (s > by_len) s = by_len;
   if (s > kNormMaxSplits) s = kNormMaxSplits;
