@@ -150,3 +150,49 @@ def test_spectral_conv_constructor_contract():
     # default mode counts follow torch-harmonics: lmax = nlat, mmax = nlon // 2 + 1
     t = mb.RealSHT(64, 128)
     assert (t.lmax, t.mmax, t.grid) == (64, 65, "equiangular")
+
+
+def test_mix_tensor_core_shape_query_and_switches():
+    """pure host logic of the C ABI: which shapes the tcgen05 mix serves (the caller then packs the weight for that precision), workspace sizes of the
+    pointwise kernels, and the run-time switches return their previous value"""
+    lib = _lib.load()
+    q = lib.b200sht_mix_uses_tensor_cores
+    assert q(_lib.OP_DHCONV, 1, 1, 73, 73, _lib.PREC_TF32) == 1
+    assert q(_lib.OP_DHCONV, 32, 1, 384, 384, _lib.PREC_TF32) == 1
+    assert q(_lib.OP_DHCONV, 3, 1, 73, 73, _lib.PREC_TF32) == 0        # batch must divide 32
+    assert q(_lib.OP_DHCONV, 1, 2, 6, 6, _lib.PREC_TF32) == 0          # group slices of 3 channels are not 16-byte aligned
+    assert q(_lib.OP_DHCONV, 1, 2, 8, 8, _lib.PREC_TF32) == 1
+    assert q(_lib.OP_DIAGONAL, 1, 1, 73, 73, _lib.PREC_TF32) == 0      # per-mode operators are bandwidth bound: one (fp32) path
+    assert q(_lib.OP_DHCONV, 1, 1, 73, 73, _lib.PREC_FP32) == 0
+    assert q(_lib.OP_DHCONV | _lib.DENSE_FLAG, 1, 1, 73, 73, _lib.PREC_TF32) == 1
+    w = lib.b200sht_pointwise_workspace_floats
+    assert w(1, 384, 721 * 1440) >= 2 * 384 and w(1, 384, 721 * 1440) % (2 * 384) == 0
+    assert w(2, 5, 63) == 2 * 10                                       # short rows: one split
+    assert w(0, 5, 63) < 0
+    old = lib.b200sht_debug_set_pdl(0)
+    assert lib.b200sht_debug_set_pdl(old) == 0
+    old = lib.b200sht_debug_set_lat_chunks(3)
+    assert lib.b200sht_debug_set_lat_chunks(old) == 3
+
+
+def test_pointwise_modules_on_cpu_are_the_torch_operators():
+    """makani_b200.norm / sfno.Conv1x1 on CPU tensors (oracle-backend reference arm, golden tests): PyTorch's own operators, same parameters and state dict"""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from makani_b200 import norm as mnorm
+    from makani_b200.sfno import Conv1x1, MLP
+
+    torch.manual_seed(333)
+    x = torch.randn(2, 6, 9, 14)
+    m, r = mnorm.InstanceNorm2d(6, eps=1e-6, affine=True), nn.InstanceNorm2d(6, eps=1e-6, affine=True)
+    assert list(m.state_dict()) == list(r.state_dict())
+    assert torch.allclose(m(x), r(x)) and torch.allclose(m(x, gelu=True), F.gelu(r(x)))
+    b = torch.randn(6)
+    assert torch.allclose(mnorm.bias_gelu(x, b), F.gelu(x + b.view(1, -1, 1, 1)))
+    c = Conv1x1(6, 10, 1, bias=True)
+    assert torch.allclose(c(x), F.conv2d(x, c.weight, c.bias), atol=1e-6)
+    mlp = MLP(6, 12, act_layer=nn.GELU)
+    assert list(mlp.state_dict()) == ["fwd.0.weight", "fwd.0.bias", "fwd.3.weight", "fwd.3.bias"]
+    ref = F.conv2d(F.gelu(F.conv2d(x, mlp.fwd[0].weight, mlp.fwd[0].bias)), mlp.fwd[3].weight, mlp.fwd[3].bias)
+    assert torch.allclose(mlp(x), ref, atol=1e-5)
