@@ -358,18 +358,17 @@ def run_gpu_arm(args):
     dp_mode = args.dp_mode
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # the gradient all-reduce runs beside two persistent kernels that leave it B200SHT_OVERLAP_SMS (8) SMs: a communicator of its own,
-        # capped at as many CTAs, so that it starts at once instead of waiting for a kernel boundary
-        try:
-            if dp_mode != "overlap":
-                raise RuntimeError("dp-mode trailing: default communicator")
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = int(os.environ.get("B200SHT_DP_MAXCTAS", os.environ.get("B200SHT_OVERLAP_SMS", "8"))) or 8
-            opts.config.min_ctas = 1
-            dp_group = dist.new_group(list(range(world)), pg_options=opts)
-        except Exception as e:   # older torch / NCCL: default communicator
-            sys.stderr.write(f"bench: NCCL communicator with max_ctas unavailable ({e}); using the default one\n")
-            dp_group = None
+        if dp_mode == "overlap":
+            # the gradient all-reduce runs beside persistent kernels that leave it B200SHT_OVERLAP_SMS (8) SMs: a communicator of its own, capped at as
+            # many CTAs.  (Measured slower than the trailing all-reduce on the default communicator, DESIGN.md section 7: not the default.)
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(os.environ.get("B200SHT_DP_MAXCTAS", os.environ.get("B200SHT_OVERLAP_SMS", "8"))) or 8
+                opts.config.min_ctas = 1
+                dp_group = dist.new_group(list(range(world)), pg_options=opts)
+            except Exception as e:   # older torch / NCCL: default communicator
+                sys.stderr.write(f"bench: NCCL communicator with max_ctas unavailable ({e}); using the default one\n")
+                dp_group = None
     wl = args.workload
     nlat_i, nlon_i, grid_i, nlat_o, nlon_o, grid_o, L, M, C = WORKLOADS[wl]
     act_dtype = torch.bfloat16 if args.act == "bf16" else torch.float32
